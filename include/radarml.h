@@ -1,0 +1,144 @@
+/*
+ * radarml.h — C ABI of libradarml.so: the B200-native replacement for the per-scan
+ * classification hot path of goruck/radar-ml (reference @ 6f7af2c).
+ *
+ * The reference is pure in-process Python and has no FFI of its own; each
+ * entry point below cites the reference call site whose arithmetic it replaces.  The Python
+ * host (radar_ml_b200/) binds these with ctypes; INTEGRATION.md shows the stub a reference
+ * maintainer would add to predict.py.
+ *
+ * Conventions
+ *   - every function returns 0 (RML_OK) or a negative rml_status; rml_last_error() gives text
+ *   - pointers named *_dev are device pointers on the context's GPU, *_host are host pointers
+ *   - the caller owns every buffer; the library owns only the context and its model copy
+ *   - device entry points are asynchronous on the given cudaStream_t and never synchronise
+ *   - a context is bound to one device and is not thread-safe; use one context per GPU
+ *   - there is NO CPU fallback anywhere: without a GPU, rml_create fails with RML_E_CUDA
+ */
+#ifndef RADARML_H_
+#define RADARML_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rml_ctx rml_ctx;
+typedef void* rml_stream; /* cudaStream_t */
+
+typedef enum rml_status {
+  RML_OK = 0,
+  RML_E_INVALID = -1,      /* bad argument / shape */
+  RML_E_CUDA = -2,         /* CUDA runtime or driver error, no usable device */
+  RML_E_UNSUPPORTED = -3,  /* e.g. zoom != 1.0 projections requested of the fused kernel */
+  RML_E_NOMODEL = -4,      /* scoring requested before rml_load_* */
+  RML_E_NONINTEGRAL = -5   /* u8 fast path saw a value that is not an integer in [0,255] */
+} rml_status;
+
+/* projection mode: predict.py:102-107 takes SLICES through the target voxel (i,j,k);
+ * BASELINE.json north_star reduces with an axis MAX.  Output shapes are identical. */
+enum { RML_MODE_MAX = 0, RML_MODE_SLICE = 1 };
+
+/* proj_mask bits, in the reference's tuple order (xz, yz, xy): common.py:40, predict.py:113 */
+enum { RML_MASK_XZ = 1, RML_MASK_YZ = 2, RML_MASK_XY = 4, RML_MASK_ALL = 7 };
+
+/* feature dtypes produced by rml_project / consumed by rml_score */
+enum {
+  RML_F32 = 0, /* float32 (n,F) exactly as common.process_samples returns (common.py:149) */
+  RML_U8 = 1   /* raw integer sensor value 0..255, K-padded rows, operand layout of the
+                  tensor-core scorer; the /255 scale is folded into the scorer */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int rml_create(int device, rml_ctx** out);
+int rml_destroy(rml_ctx* ctx);
+const char* rml_last_error(const rml_ctx* ctx); /* ctx may be NULL: last create() error */
+int rml_version(void);
+
+/* ---- layout: common.py:25-27 arena -> cube dims (size_x,size_y,size_z) = (22,31,176) ---- */
+int rml_set_arena(rml_ctx* ctx, int size_x, int size_y, int size_z);
+/* spherical bounds used by calculate_matrix_indices (common.py:25-27 R/THETA/PHI MIN,MAX) */
+int rml_set_arena_bounds(rml_ctx* ctx, double r_min, double r_max, double theta_min,
+                         double theta_max, double phi_min, double phi_max);
+int rml_feature_len(const rml_ctx* ctx, uint32_t mask);    /* F for a mask (10010 for all)   */
+int rml_feature_stride(const rml_ctx* ctx, uint32_t mask, int dtype); /* elements per row    */
+
+/* Per-feature affine (x - offset) / scale applied by rml_project for RML_F32 output.
+ * scalar form covers common.py:148 (/255., offset 0) and dnn.py:202-205 ((p-127.5)/127.5). */
+int rml_set_affine(rml_ctx* ctx, float offset, float scale, int enabled);
+
+/* ---- model load: what predict.py:224-225 unpickles ------------------------------------ */
+/* CalibratedClassifierCV(prefit SVC rbf) built at train.py:478-479, 723-724.
+ * sv (n_sv,F) row-major, dual_coef (n_classes-1,n_sv), rho (n_classes*(n_classes-1)/2)
+ * (= -intercept_), n_support (n_classes), platt a/b per class in estimator.classes_ order
+ * (one pair when n_classes == 2).  All host pointers, float64 like sklearn holds them.
+ * feature_scale: the value the training features were divided by (255, common.py:31). */
+int rml_load_svc_rbf(rml_ctx* ctx, int n_classes, int F, int n_sv, const int32_t* n_support,
+                     const double* sv_host, const double* dual_coef_host, const double* rho_host,
+                     double gamma, const double* platt_a_host, const double* platt_b_host,
+                     double feature_scale);
+/* SGDClassifier(loss='log') alternative, train.py:368-369 (deployed in predict.log:9). */
+int rml_load_linear(rml_ctx* ctx, int n_classes, int F, const double* coef_host,
+                    const double* intercept_host, const double* platt_a_host,
+                    const double* platt_b_host, double feature_scale);
+/* 1 when the loaded SVC's support vectors are integers/feature_scale (u8 tensor path usable) */
+int rml_model_is_integral(const rml_ctx* ctx);
+
+/* ---- K1: predict.py:102-107 + common.py:141-149 (projection, concat, scale) ------------ */
+/* cubes_dev: float32 [B][size_x][size_y][size_z] (predict.py:91 layout, z fastest).
+ * ijk_dev: int32 [B][3] target voxel for RML_MODE_SLICE (common.py:106-121), else NULL.
+ * feats_dev: [B][rml_feature_stride()] of dtype.  norms_dev: int32 [B] sum of squares of the
+ * u8 row (RML_U8 only, may be NULL). */
+int rml_project(rml_ctx* ctx, const float* cubes_dev, int64_t B, int mode, const int32_t* ijk_dev,
+                uint32_t mask, int dtype, void* feats_dev, int32_t* norms_dev, rml_stream stream);
+/* common.process_samples on already-extracted projections (common.py:123-149, zoom 1.0):
+ * xz [B][sx][sz], yz [B][sy][sz], xy [B][sx][sy] float32 device arrays (NULL if masked out). */
+int rml_process_samples(rml_ctx* ctx, const float* xz_dev, const float* yz_dev,
+                        const float* xy_dev, int64_t B, uint32_t mask, int scale,
+                        float* feats_dev, rml_stream stream);
+/* common.calculate_matrix_indices (common.py:106-121) for B targets: xyz_dev float64 [B][3] */
+int rml_matrix_indices(rml_ctx* ctx, const double* xyz_dev, int64_t B, int32_t* ijk_dev,
+                       rml_stream stream);
+
+/* ---- K2: predict.py:56-70 classifier() -> model.predict_proba chain -------------------- */
+/* feats_dev as written by rml_project (dtype RML_U8 needs norms_dev) or float32 (n,F)
+ * features already scaled like common.process_samples(scale=True).
+ * proba_dev float32 [B][n_classes]; decision_dev float32 [B][n_classes] OvR decision values
+ * (nullable; [B] when n_classes == 2); label_dev int32 [B] = argmax; known_dev uint8 [B] =
+ * (max proba >= min_proba), i.e. name != 'Unknown' at predict.py:65-68. */
+int rml_score(rml_ctx* ctx, const void* feats_dev, int dtype, const int32_t* norms_dev, int64_t B,
+              double min_proba, float* proba_dev, float* decision_dev, int32_t* label_dev,
+              uint8_t* known_dev, rml_stream stream);
+
+/* (n,F) float32 features scaled like common.process_samples(scale=True) -> the u8 operand
+ * rows + norms rml_score(RML_U8) consumes.  Values that are not exactly
+ * float32(u)/float32(feature_scale), u integer in [0,255], are reported by rml_check_status
+ * (RML_E_NONINTEGRAL): score those features as RML_F32 instead. */
+int rml_quantize_features(rml_ctx* ctx, const float* feats_dev, int64_t B, int F,
+                          uint8_t* feats_u8_dev, int32_t* norms_dev, rml_stream stream);
+
+/* ---- K1 -> K2 fused pipeline: one predict.py:93-119 iteration for B scans -------------- */
+/* workspace: rml_predict_workspace_bytes(ctx, B) bytes of device memory (feature staging). */
+size_t rml_predict_workspace_bytes(const rml_ctx* ctx, int64_t B);
+int rml_predict(rml_ctx* ctx, const float* cubes_dev, int64_t B, int mode, const int32_t* ijk_dev,
+                uint32_t mask, double min_proba, void* workspace_dev, float* proba_dev,
+                int32_t* label_dev, uint8_t* known_dev, rml_stream stream);
+/* Same, HOST buffers in and out (cubes_host pinned or pageable float32; results to host).
+ * Streams the batch through the GPU in chunks with H2D / compute / D2H overlapped and
+ * returns after the results are in host memory.  This is the e2e entry bench.py times. */
+int rml_predict_host(rml_ctx* ctx, const float* cubes_host, int64_t B, int mode,
+                     const int32_t* ijk_host, uint32_t mask, double min_proba, float* proba_host,
+                     int32_t* label_host, uint8_t* known_host);
+
+/* ---- status of the last asynchronous work (non-integral count seen by the u8 path) ----- */
+int rml_check_status(rml_ctx* ctx, rml_stream stream); /* synchronises the stream */
+
+/* number of kernels this library launched since create (bench.py "gpu_launches") */
+int64_t rml_launch_count(const rml_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADARML_H_ */

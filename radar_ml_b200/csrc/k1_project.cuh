@@ -1,0 +1,498 @@
+// K1 project_scale — replaces predict.py:102-107 (projection extraction) and
+// common.py:141-149 (concat xz|yz|xy, optional /RADAR_MAX) for batches of radar cubes.
+//
+// Fast path (arena 22x31x176, common.py:25-27): one persistent CTA per SM streams the cube
+// as 22 contiguous i-slabs (31x176 fp32 = 21 824 B) through a ring of shared-memory stages
+// filled by 1-D bulk async copies (UBLKCP) that complete on mbarriers.  Warp roles:
+//   warps 0..7  "row" warps: own 4 rows j of every slab; running max over i (yz) lives in
+//               registers, the per-row max over k (xy) is one CREDUX.MAX.F32 per row
+//   warps 8..9  "column" warps: alternate slabs, max over j for every k (xz)
+//   warp 10     producer: issues the bulk copies (one elected lane)
+//   warp 11     flusher: writes the finished feature row back (bulk S2G for u8)
+// One HBM read of the cube, no re-reads; output is 2 % (u8) / 8 % (f32) of the input bytes.
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "ptx.cuh"
+
+namespace rml {
+
+constexpr int kSX = 22, kSY = 31, kSZ = 176;
+constexpr int kSlabElems = kSY * kSZ;              // 5456
+constexpr int kSlabBytes = kSlabElems * 4;         // 21824
+constexpr int kCubeElems = kSX * kSlabElems;       // 120032
+constexpr int kFxz = kSX * kSZ, kFyz = kSY * kSZ, kFxy = kSX * kSY;  // 3872, 5456, 682
+constexpr int kRowWarps = 8, kColWarps = 2;
+constexpr int kK1Threads = (kRowWarps + kColWarps + 2) * 32;  // 384
+constexpr int kK1Stages = 6;
+
+struct K1Params {
+  const float* cubes;
+  void* feats;        // [B][stride] u8 or f32
+  int32_t* norms;     // [B] (u8 only, nullable)
+  unsigned int* status;  // [0] += number of non-integral values seen (u8 only)
+  int64_t B;
+  int stride;         // elements per output row
+  int F;              // valid features per row
+  uint32_t mask;
+  float offset, scale;  // f32 output: (v - offset) / scale when affine != 0
+  int affine;
+};
+
+template <typename OutT>
+struct Emit;
+
+template <>
+struct Emit<uint8_t> {
+  // raw integer value; flags anything that is not an integer in [0,255]
+  static __device__ __forceinline__ uint32_t cvt(float v, uint32_t& bad) {
+    uint32_t u = __float2uint_rn(v);
+    bad |= (static_cast<float>(u) != v) | (u > 255u);
+    return u & 255u;
+  }
+  static __device__ __forceinline__ void put2(uint8_t* stg, int idx, float a, float b,
+                                              const K1Params&, uint32_t& sumsq, uint32_t& bad) {
+    uint32_t ua = cvt(a, bad), ub = cvt(b, bad);
+    sumsq += ua * ua + ub * ub;
+    *reinterpret_cast<uint16_t*>(stg + idx) = static_cast<uint16_t>(ua | (ub << 8));
+  }
+  static __device__ __forceinline__ void put1(uint8_t* stg, int idx, float a, const K1Params&,
+                                              uint32_t& sumsq, uint32_t& bad) {
+    uint32_t ua = cvt(a, bad);
+    sumsq += ua * ua;
+    stg[idx] = static_cast<uint8_t>(ua);
+  }
+};
+
+template <>
+struct Emit<float> {
+  static __device__ __forceinline__ float cvt(float v, const K1Params& p) {
+    // common.py:148 is an IEEE float32 true division (x/255f != x*(1/255f) for 126 of 256 ints)
+    return p.affine ? __fdiv_rn(v - p.offset, p.scale) : v;
+  }
+  static __device__ __forceinline__ void put2(float* stg, int idx, float a, float b,
+                                              const K1Params& p, uint32_t&, uint32_t&) {
+    *reinterpret_cast<float2*>(stg + idx) = make_float2(cvt(a, p), cvt(b, p));
+  }
+  static __device__ __forceinline__ void put1(float* stg, int idx, float a, const K1Params& p,
+                                              uint32_t&, uint32_t&) {
+    stg[idx] = cvt(a, p);
+  }
+};
+
+template <typename OutT>
+__host__ __device__ constexpr int k1_staging_bytes() {
+  // u8: K-padded row (10112 B for the full mask); f32: 10010*4 rounded up to 128
+  return sizeof(OutT) == 1 ? 10112 : 40064;
+}
+template <typename OutT>
+__host__ __device__ constexpr int k1_smem_bytes() {
+  return kK1Stages * kSlabBytes + 2 * k1_staging_bytes<OutT>() + 256;
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* slabs = reinterpret_cast<float*>(smem);
+  OutT* stg0 = reinterpret_cast<OutT*>(smem + kK1Stages * kSlabBytes);
+  constexpr int kStgBytes = k1_staging_bytes<OutT>();
+  unsigned char* tail = smem + kK1Stages * kSlabBytes + 2 * kStgBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);   // [kK1Stages]
+  uint64_t* empty = full + kK1Stages;                   // [kK1Stages]
+  uint64_t* done = empty + kK1Stages;                   // [2] scan finished in staging buf
+  uint64_t* sfree = done + 2;                           // [2] staging buf flushed
+  uint32_t* norm_acc = reinterpret_cast<uint32_t*>(sfree + 2);  // [2]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kK1Stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kRowWarps + 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&done[b], kRowWarps + kColWarps);
+      mbar_init(&sfree[b], 1);
+      norm_acc[b] = 0;
+    }
+    fence_barrier_init();
+  }
+  // zero both staging rows once: pad bytes [F, stride) stay zero for the whole kernel
+  for (int i = threadIdx.x; i < 2 * kStgBytes / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(stg0)[i] = 0u;
+  __syncthreads();
+
+  const int off_xz = 0;
+  const int off_yz = (p.mask & 1u) ? kFxz : 0;
+  const int off_xy = off_yz + ((p.mask & 2u) ? kFyz : 0);
+  const float NEG = -FLT_MAX;
+
+  uint32_t it = 0;  // running slab counter (identical in every role)
+  uint32_t t = 0;   // running scan counter of this CTA
+
+  if (warp < kRowWarps) {
+    // ------------------------------------------------------------------ row warps
+    const int j0 = warp * 4;
+    const int nrows = (warp == kRowWarps - 1) ? (kSY - j0) : 4;
+    float yz[4][6];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int m = 0; m < 6; ++m) yz[r][m] = NEG;
+    uint32_t sumsq = 0, bad = 0;
+    for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++t) {
+      const int buf = t & 1;
+      OutT* stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
+      mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
+      for (int i = 0; i < kSX; ++i, ++it) {
+        const int stage = it % kK1Stages;
+        mbar_wait(&full[stage], (it / kK1Stages) & 1);
+        const float* slab = slabs + stage * kSlabElems;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (r < nrows) {
+            const float2* row = reinterpret_cast<const float2*>(slab + (j0 + r) * kSZ);
+            const float2 a = row[lane];
+            const float2 c = row[32 + lane];
+            float2 e = make_float2(NEG, NEG);
+            if (lane < 24) e = row[64 + lane];
+            yz[r][0] = fmaxf(yz[r][0], a.x);
+            yz[r][1] = fmaxf(yz[r][1], a.y);
+            yz[r][2] = fmaxf(yz[r][2], c.x);
+            yz[r][3] = fmaxf(yz[r][3], c.y);
+            yz[r][4] = fmaxf(yz[r][4], e.x);
+            yz[r][5] = fmaxf(yz[r][5], e.y);
+            float m = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(c.x, c.y)), fmaxf(e.x, e.y));
+            m = warp_max_f32(m);
+            if (lane == 0 && (p.mask & 4u))
+              Emit<OutT>::put1(stg, off_xy + i * kSY + j0 + r, m, p, sumsq, bad);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+      }
+      // end of scan: the running max over i is the yz projection
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (r < nrows) {
+          if (p.mask & 2u) {
+            const int base = off_yz + (j0 + r) * kSZ + 2 * lane;
+            Emit<OutT>::put2(stg, base, yz[r][0], yz[r][1], p, sumsq, bad);
+            Emit<OutT>::put2(stg, base + 64, yz[r][2], yz[r][3], p, sumsq, bad);
+            if (lane < 24) Emit<OutT>::put2(stg, base + 128, yz[r][4], yz[r][5], p, sumsq, bad);
+          }
+#pragma unroll
+          for (int m = 0; m < 6; ++m) yz[r][m] = NEG;
+        }
+      }
+      if (sizeof(OutT) == 1) {
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, sumsq);
+        if (lane == 0 && tot) atomicAdd(&norm_acc[buf], tot);
+        sumsq = 0;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&done[buf]);
+    }
+    if (bad) atomicAdd(p.status, 1u);
+  } else if (warp < kRowWarps + kColWarps) {
+    // ------------------------------------------------------------------ column warps
+    const int c = warp - kRowWarps;
+    uint32_t sumsq = 0, bad = 0;
+    for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++t) {
+      const int buf = t & 1;
+      OutT* stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
+      mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
+      for (int i = 0; i < kSX; ++i, ++it) {
+        if ((i & 1) != c) continue;
+        const int stage = it % kK1Stages;
+        mbar_wait(&full[stage], (it / kK1Stages) & 1);
+        if (p.mask & 1u) {
+          const float2* slab = reinterpret_cast<const float2*>(slabs + stage * kSlabElems);
+          float m0 = NEG, m1 = NEG, m2 = NEG, m3 = NEG, m4 = NEG, m5 = NEG;
+#pragma unroll 8
+          for (int j = 0; j < kSY; ++j) {
+            const float2* row = slab + j * (kSZ / 2);
+            const float2 a = row[lane];
+            const float2 cc = row[32 + lane];
+            float2 e = make_float2(NEG, NEG);
+            if (lane < 24) e = row[64 + lane];
+            m0 = fmaxf(m0, a.x);
+            m1 = fmaxf(m1, a.y);
+            m2 = fmaxf(m2, cc.x);
+            m3 = fmaxf(m3, cc.y);
+            m4 = fmaxf(m4, e.x);
+            m5 = fmaxf(m5, e.y);
+          }
+          const int base = off_xz + i * kSZ + 2 * lane;
+          Emit<OutT>::put2(stg, base, m0, m1, p, sumsq, bad);
+          Emit<OutT>::put2(stg, base + 64, m2, m3, p, sumsq, bad);
+          if (lane < 24) Emit<OutT>::put2(stg, base + 128, m4, m5, p, sumsq, bad);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+      }
+      if (sizeof(OutT) == 1) {
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, sumsq);
+        if (lane == 0 && tot) atomicAdd(&norm_acc[buf], tot);
+        sumsq = 0;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&done[buf]);
+    }
+    if (bad) atomicAdd(p.status, 1u);
+  } else if (warp == kRowWarps + kColWarps) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_first();
+      for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+        const float* cube = p.cubes + b * kCubeElems;
+        for (int i = 0; i < kSX; ++i, ++it) {
+          const int stage = it % kK1Stages;
+          mbar_wait(&empty[stage], ((it / kK1Stages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[stage], kSlabBytes);
+          bulk_g2s(slabs + stage * kSlabElems, cube + i * kSlabElems, kSlabBytes, &full[stage], pol);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ flusher
+    for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++t) {
+      const int buf = t & 1;
+      OutT* stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
+      mbar_wait(&done[buf], (t >> 1) & 1);
+      if (sizeof(OutT) == 1) {
+        if (lane == 0) {
+          bulk_s2g(reinterpret_cast<uint8_t*>(p.feats) + b * p.stride, stg, p.stride);
+          bulk_commit();
+          if (p.norms) p.norms[b] = static_cast<int32_t>(norm_acc[buf]);
+          norm_acc[buf] = 0;
+          bulk_wait_read<0>();
+          mbar_arrive(&sfree[buf]);
+        }
+      } else {
+        // (n,F) float32 rows are only 8-byte aligned (F*4 = 40040): plain coalesced stores
+        float* out = reinterpret_cast<float*>(p.feats) + b * static_cast<int64_t>(p.stride);
+        const float* src = reinterpret_cast<const float*>(stg);
+        for (int idx = 2 * lane; idx < p.F; idx += 64)
+          *reinterpret_cast<float2*>(out + idx) = *reinterpret_cast<const float2*>(src + idx);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sfree[buf]);
+      }
+    }
+    if (sizeof(OutT) == 1 && lane == 0) bulk_wait_all<0>();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic kernels: any arena, MAX or SLICE (predict.py:102-107 semantics incl. numpy negative
+// index wrap).  One CTA per scan; SLICE touches only the three planes it needs.
+struct K1GenParams {
+  const float* cubes;
+  const int32_t* ijk;  // [B][3] (slice)
+  void* feats;
+  int32_t* norms;
+  unsigned int* status;
+  int64_t B;
+  int sx, sy, sz;
+  int stride, F;
+  uint32_t mask;
+  float offset, scale;
+  int affine;
+  int mode;
+};
+
+template <typename OutT>
+__device__ __forceinline__ void gen_put(OutT* out, int idx, float v, const K1GenParams& p,
+                                        uint32_t& sumsq, uint32_t& bad);
+template <>
+__device__ __forceinline__ void gen_put<uint8_t>(uint8_t* out, int idx, float v,
+                                                 const K1GenParams&, uint32_t& sumsq,
+                                                 uint32_t& bad) {
+  uint32_t u = Emit<uint8_t>::cvt(v, bad);
+  sumsq += u * u;
+  out[idx] = static_cast<uint8_t>(u);
+}
+template <>
+__device__ __forceinline__ void gen_put<float>(float* out, int idx, float v, const K1GenParams& p,
+                                               uint32_t&, uint32_t&) {
+  out[idx] = p.affine ? __fdiv_rn(v - p.offset, p.scale) : v;
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) k1_project_generic(const K1GenParams p) {
+  __shared__ uint32_t s_sum;
+  const int sx = p.sx, sy = p.sy, sz = p.sz;
+  const int fxz = sx * sz, fyz = sy * sz, fxy = sx * sy;
+  const int off_yz = (p.mask & 1u) ? fxz : 0;
+  const int off_xy = off_yz + ((p.mask & 2u) ? fyz : 0);
+  for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const float* cube = p.cubes + b * static_cast<int64_t>(sx) * sy * sz;
+    OutT* out = reinterpret_cast<OutT*>(p.feats) + b * static_cast<int64_t>(p.stride);
+    uint32_t sumsq = 0, bad = 0;
+    int ti = 0, tj = 0, tk = 0;
+    bool ok = true;
+    if (p.mode == 1) {
+      ti = p.ijk[b * 3 + 0];
+      tj = p.ijk[b * 3 + 1];
+      tk = p.ijk[b * 3 + 2];
+      // numpy semantics: negative indices wrap once, anything else is an IndexError
+      if (ti < 0) ti += sx;
+      if (tj < 0) tj += sy;
+      if (tk < 0) tk += sz;
+      ok = ti >= 0 && ti < sx && tj >= 0 && tj < sy && tk >= 0 && tk < sz;
+      if (!ok) {
+        if (threadIdx.x == 0) atomicAdd(p.status + 1, 1u);
+        ti = tj = tk = 0;
+      }
+    }
+    if (p.mask & 1u) {
+      for (int e = threadIdx.x; e < fxz; e += blockDim.x) {
+        const int i = e / sz, k = e - i * sz;
+        float v;
+        if (p.mode == 1) {
+          v = cube[(static_cast<int64_t>(i) * sy + tj) * sz + k];
+        } else {
+          v = -FLT_MAX;
+          for (int j = 0; j < sy; ++j) v = fmaxf(v, cube[(static_cast<int64_t>(i) * sy + j) * sz + k]);
+        }
+        gen_put<OutT>(out, e, ok ? v : 0.f, p, sumsq, bad);
+      }
+    }
+    if (p.mask & 2u) {
+      for (int e = threadIdx.x; e < fyz; e += blockDim.x) {
+        const int j = e / sz, k = e - j * sz;
+        float v;
+        if (p.mode == 1) {
+          v = cube[(static_cast<int64_t>(ti) * sy + j) * sz + k];
+        } else {
+          v = -FLT_MAX;
+          for (int i = 0; i < sx; ++i) v = fmaxf(v, cube[(static_cast<int64_t>(i) * sy + j) * sz + k]);
+        }
+        gen_put<OutT>(out, off_yz + e, ok ? v : 0.f, p, sumsq, bad);
+      }
+    }
+    if (p.mask & 4u) {
+      if (p.mode == 1) {
+        for (int e = threadIdx.x; e < fxy; e += blockDim.x) {
+          const float v = cube[static_cast<int64_t>(e) * sz + tk];
+          gen_put<OutT>(out, off_xy + e, ok ? v : 0.f, p, sumsq, bad);
+        }
+      } else {
+        // one warp per (i,j) row: coalesced read along k, shuffle max
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        for (int e = warp; e < fxy; e += nw) {
+          const float* row = cube + static_cast<int64_t>(e) * sz;
+          float v = -FLT_MAX;
+          for (int k = lane; k < sz; k += 32) v = fmaxf(v, row[k]);
+          v = warp_max_f32(v);
+          if (lane == 0) gen_put<OutT>(out, off_xy + e, v, p, sumsq, bad);
+        }
+      }
+    }
+    if (sizeof(OutT) == 1) {
+      // zero the K padding so the row is fully defined
+      for (int e = p.F + threadIdx.x; e < p.stride; e += blockDim.x) out[e] = 0;
+      const uint32_t tot = __reduce_add_sync(0xffffffffu, sumsq);
+      if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&s_sum, tot);
+      __syncthreads();
+      if (threadIdx.x == 0 && p.norms) p.norms[b] = static_cast<int32_t>(s_sum);
+      if (bad) atomicAdd(p.status, 1u);
+    }
+    __syncthreads();
+  }
+}
+
+// common.process_samples on already extracted projections (common.py:141-149, zoom 1.0).
+struct PsParams {
+  const float* proj[3];  // xz, yz, xy (nullable when masked out)
+  int len[3];            // elements per sample of each projection
+  int off[3];            // output offset of each projection
+  float* feats;
+  int64_t B;
+  int F;
+  int scale;
+  float scale_value;
+};
+__global__ void __launch_bounds__(256) k1_process_samples(const PsParams p) {
+  const int64_t total = p.B * static_cast<int64_t>(p.F);
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = e / p.F;
+    const int f = static_cast<int>(e - b * p.F);
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (p.proj[q] && f >= p.off[q] && f < p.off[q] + p.len[q])
+        v = p.proj[q][b * p.len[q] + (f - p.off[q])];
+    p.feats[e] = p.scale ? __fdiv_rn(v, p.scale_value) : v;
+  }
+}
+
+// (n,F) float32 features scaled like common.process_samples(scale=True) -> raw u8 operand rows
+// + integer norms for the tensor-core scorer.  A value qualifies when it is exactly
+// float32(u)/float32(scale) for an integer u in [0,255]; anything else bumps status[0].
+struct QuantParams {
+  const float* feats;
+  uint8_t* out;
+  int32_t* norms;
+  unsigned int* status;
+  int64_t B;
+  int F, stride;
+  float scale;
+};
+__global__ void __launch_bounds__(256) k1_quantize(const QuantParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = blockIdx.x * 8ll + warp;
+  if (b >= p.B) return;
+  const float* x = p.feats + b * p.F;
+  uint8_t* o = p.out + b * p.stride;
+  uint32_t sumsq = 0, bad = 0;
+  for (int f = lane; f < p.stride; f += 32) {
+    uint32_t u = 0;
+    if (f < p.F) {
+      const float v = x[f];
+      u = __float2uint_rn(v * p.scale);
+      bad |= (u > 255u) | (__fdiv_rn(static_cast<float>(u), p.scale) != v);
+      u &= 255u;
+    }
+    o[f] = static_cast<uint8_t>(u);
+    sumsq += u * u;
+  }
+  const uint32_t tot = __reduce_add_sync(0xffffffffu, sumsq);
+  if (lane == 0) p.norms[b] = static_cast<int32_t>(tot);
+  if (bad) atomicAdd(p.status, 1u);
+}
+
+// common.calculate_matrix_indices (common.py:106-121 + 93-97), float64 like numpy.
+struct IdxParams {
+  const double* xyz;
+  int32_t* ijk;
+  int64_t B;
+  int sx, sy, sz;
+  double r_min, r_max, th_min, th_max, ph_min, ph_max;
+};
+__global__ void __launch_bounds__(128) k1_matrix_indices(const IdxParams p) {
+  const int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (b >= p.B) return;
+  const double x = p.xyz[b * 3 + 0], y = p.xyz[b * 3 + 1], z = p.xyz[b * 3 + 2];
+  const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+  const double k180_pi = 180.0 / 3.141592653589793238462643383279502884;
+  const double phi = __dmul_rn(atan2(y, z), k180_pi);
+  const double theta = __dmul_rn(asin(x / r), k180_pi);
+  // int() truncates toward zero; evaluation order as written in common.py:118-120
+  const double fi = __dmul_rn(theta - p.th_min, static_cast<double>(p.sx - 1)) / (p.th_max - p.th_min);
+  const double fj = __dmul_rn(phi - p.ph_min, static_cast<double>(p.sy - 1)) / (p.ph_max - p.ph_min);
+  const double fk = __dmul_rn(r - p.r_min, static_cast<double>(p.sz - 1)) / (p.r_max - p.r_min);
+  p.ijk[b * 3 + 0] = static_cast<int32_t>(fi);
+  p.ijk[b * 3 + 1] = static_cast<int32_t>(fj);
+  p.ijk[b * 3 + 2] = static_cast<int32_t>(fk);
+}
+
+}  // namespace rml

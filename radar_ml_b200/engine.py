@@ -1,0 +1,277 @@
+"""Engine — one libradarml context per GPU; torch tensors are only device containers.
+
+Batched extensions of the reference seam: ``project`` (predict.py:102-107 +
+common.py:141-149), ``score`` (predict.py:56-70) and ``predict`` (one predict.py:93-119
+iteration for B scans).  Every call goes through the C ABI in include/radarml.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import F32, MASK_ALL, MODE_MAX, MODE_SLICE, U8, NonIntegralInput, RadarMLError, check
+
+SX, SY, SZ = 22, 31, 176  # common.py:25-27 -> predict.py:74-76
+
+
+def mask_bits(proj_mask) -> int:
+    """ProjMask(xz, yz, xy) (common.py:40) -> bit0 xz, bit1 yz, bit2 xy."""
+    if isinstance(proj_mask, int):
+        return proj_mask
+    xz, yz, xy = proj_mask
+    return (1 if xz else 0) | (2 if yz else 0) | (4 if xy else 0)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RadarMLError(_lib.E_CUDA, "no CUDA device: radar_ml_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        self.ctx = C.c_void_p()
+        rc = self.lib.rml_create(device, C.byref(self.ctx))
+        if rc != 0:
+            msg = self.lib.rml_last_error(None)
+            raise RadarMLError(rc, msg.decode() if msg else "rml_create failed")
+        self.params = None
+        self.dims = (SX, SY, SZ)
+        self._work = None
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx:
+            self.lib.rml_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ configuration
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_arena(self, sx, sy, sz):
+        check(self.ctx, self.lib.rml_set_arena(self.ctx, sx, sy, sz))
+        self.dims = (sx, sy, sz)
+
+    def set_arena_bounds(self, r_min, r_max, theta_min, theta_max, phi_min, phi_max):
+        check(self.ctx, self.lib.rml_set_arena_bounds(self.ctx, r_min, r_max, theta_min, theta_max,
+                                                      phi_min, phi_max))
+
+    def set_affine(self, offset=0.0, scale=255.0, enabled=True):
+        check(self.ctx, self.lib.rml_set_affine(self.ctx, offset, scale, 1 if enabled else 0))
+
+    def feature_len(self, mask=MASK_ALL):
+        return self.lib.rml_feature_len(self.ctx, mask_bits(mask))
+
+    def feature_stride(self, mask=MASK_ALL, dtype=F32):
+        return self.lib.rml_feature_stride(self.ctx, mask_bits(mask), dtype)
+
+    def load_model(self, p):
+        """p: radar_ml_b200.model.ModelParams."""
+        if p.kind == "svc_rbf":
+            ns = np.ascontiguousarray(p.n_support, dtype=np.int32)
+            sv = np.ascontiguousarray(p.sv, dtype=np.float64)
+            dc = np.ascontiguousarray(p.dual_coef, dtype=np.float64)
+            rho = np.ascontiguousarray(p.rho, dtype=np.float64)
+            a = np.ascontiguousarray(p.platt_a, dtype=np.float64)
+            b = np.ascontiguousarray(p.platt_b, dtype=np.float64)
+            check(self.ctx, self.lib.rml_load_svc_rbf(
+                self.ctx, p.n_classes, p.n_features, sv.shape[0], _np_ptr(ns), _np_ptr(sv),
+                _np_ptr(dc), _np_ptr(rho), float(p.gamma), _np_ptr(a), _np_ptr(b),
+                float(p.feature_scale)))
+        elif p.kind == "linear":
+            coef = np.ascontiguousarray(p.coef, dtype=np.float64)
+            ic = np.ascontiguousarray(p.intercept, dtype=np.float64)
+            a = np.ascontiguousarray(p.platt_a, dtype=np.float64)
+            b = np.ascontiguousarray(p.platt_b, dtype=np.float64)
+            check(self.ctx, self.lib.rml_load_linear(self.ctx, p.n_classes, p.n_features,
+                                                     _np_ptr(coef), _np_ptr(ic), _np_ptr(a),
+                                                     _np_ptr(b), float(p.feature_scale)))
+        else:
+            raise ValueError(p.kind)
+        self.params = p
+
+    @property
+    def model_is_integral(self) -> bool:
+        return bool(self.lib.rml_model_is_integral(self.ctx))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.rml_launch_count(self.ctx))
+
+    def check_status(self):
+        """Synchronise and raise if the u8 path met non-integral data / bad slice indices."""
+        check(self.ctx, self.lib.rml_check_status(self.ctx, self._stream()))
+
+    # ------------------------------------------------------------------ K1
+    def _check_cubes(self, cubes):
+        sx, sy, sz = self.dims
+        if not (isinstance(cubes, torch.Tensor) and cubes.is_cuda and cubes.dtype == torch.float32
+                and cubes.is_contiguous() and cubes.dim() == 4
+                and tuple(cubes.shape[1:]) == (sx, sy, sz)):
+            raise ValueError("cubes must be a contiguous CUDA float32 tensor [B,%d,%d,%d]"
+                             % (sx, sy, sz))
+        if cubes.device != self.device:
+            raise ValueError("cubes are on %s, engine on %s" % (cubes.device, self.device))
+
+    def project(self, cubes, mode="max", ijk=None, mask=MASK_ALL, dtype=F32, out=None, norms=None):
+        """cubes [B,sx,sy,sz] -> features [B,stride] (+ int32 norms for U8)."""
+        self._check_cubes(cubes)
+        m = mask_bits(mask)
+        B = cubes.shape[0]
+        stride = self.feature_stride(m, dtype)
+        if out is None:
+            out = torch.empty((B, stride), device=self.device,
+                              dtype=torch.uint8 if dtype == U8 else torch.float32)
+        if dtype == U8 and norms is None:
+            norms = torch.empty((B,), device=self.device, dtype=torch.int32)
+        md = MODE_MAX if mode in ("max", MODE_MAX) else MODE_SLICE
+        if md == MODE_SLICE:
+            if ijk is None:
+                raise ValueError("slice mode needs ijk [B,3] int32")
+            ijk = ijk.to(device=self.device, dtype=torch.int32).contiguous()
+        check(self.ctx, self.lib.rml_project(self.ctx, _ptr(cubes), B, md, _ptr(ijk), m, dtype,
+                                             _ptr(out), _ptr(norms), self._stream()))
+        return (out, norms) if dtype == U8 else out
+
+    def process_samples(self, xz, yz, xy, mask=MASK_ALL, scale=False):
+        """common.process_samples on device projections (zoom 1.0)."""
+        m = mask_bits(mask)
+        ref = next(t for t in (xz, yz, xy) if t is not None)
+        B = ref.shape[0]
+        F = self.feature_len(m)
+        out = torch.empty((B, F), device=self.device, dtype=torch.float32)
+        check(self.ctx, self.lib.rml_process_samples(self.ctx, _ptr(xz), _ptr(yz), _ptr(xy), B, m,
+                                                     1 if scale else 0, _ptr(out), self._stream()))
+        return out
+
+    def matrix_indices(self, xyz):
+        """xyz [B,3] float64 CUDA -> ijk [B,3] int32 (common.calculate_matrix_indices)."""
+        xyz = xyz.to(device=self.device, dtype=torch.float64).contiguous()
+        out = torch.empty((xyz.shape[0], 3), device=self.device, dtype=torch.int32)
+        check(self.ctx, self.lib.rml_matrix_indices(self.ctx, _ptr(xyz), xyz.shape[0], _ptr(out),
+                                                    self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ K2
+    def score(self, feats, norms=None, min_proba=0.7, want_decision=False):
+        """features -> (proba [B,C] f32, label [B] i32, known [B] bool[, decision])."""
+        if self.params is None:
+            raise RadarMLError(_lib.E_NOMODEL, "no model loaded")
+        B = feats.shape[0]
+        Cn = self.params.n_classes
+        dtype = U8 if feats.dtype == torch.uint8 else F32
+        proba = torch.empty((B, Cn), device=self.device, dtype=torch.float32)
+        label = torch.empty((B,), device=self.device, dtype=torch.int32)
+        known = torch.empty((B,), device=self.device, dtype=torch.uint8)
+        dec = None
+        if want_decision:
+            dec = torch.empty((B,) if Cn == 2 else (B, Cn), device=self.device, dtype=torch.float32)
+        check(self.ctx, self.lib.rml_score(self.ctx, _ptr(feats), dtype, _ptr(norms), B,
+                                           float(min_proba), _ptr(proba), _ptr(dec), _ptr(label),
+                                           _ptr(known), self._stream()))
+        res = (proba, label, known.bool())
+        return res + (dec,) if want_decision else res
+
+    def quantize(self, feats_f32):
+        """(n,F) float32 scaled features -> (u8 rows, norms); see rml_quantize_features."""
+        B, F = feats_f32.shape
+        stride = (F + 127) // 128 * 128
+        out = torch.empty((B, stride), device=self.device, dtype=torch.uint8)
+        norms = torch.empty((B,), device=self.device, dtype=torch.int32)
+        check(self.ctx, self.lib.rml_quantize_features(self.ctx, _ptr(feats_f32), B, F, _ptr(out),
+                                                       _ptr(norms), self._stream()))
+        return out, norms
+
+    def score_features_host(self, X: np.ndarray, min_proba=0.7):
+        """model.predict_proba(X) for host features as common.process_samples(scale=True) makes
+        them.  Integral features of an integral model run on the tensor cores; anything else
+        runs the exact general-precision kernel (decided by an explicit device-side check)."""
+        x = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).to(self.device)
+        use_u8 = self.params.kind == "svc_rbf" and self.model_is_integral
+        if use_u8:
+            q, norms = self.quantize(x)
+            try:
+                self.check_status()
+            except NonIntegralInput:
+                use_u8 = False
+        if use_u8:
+            proba, label, known = self.score(q, norms, min_proba)
+        else:
+            proba, label, known = self.score(x, None, min_proba)
+        torch.cuda.synchronize(self.device)
+        return proba.cpu().numpy(), label.cpu().numpy(), known.cpu().numpy()
+
+    # ------------------------------------------------------------------ K1 -> K2
+    def workspace(self, B):
+        need = int(self.lib.rml_predict_workspace_bytes(self.ctx, B))
+        if self._work is None or self._work.numel() < need:
+            self._work = torch.empty((need,), device=self.device, dtype=torch.uint8)
+        return self._work
+
+    def predict(self, cubes, mode="max", ijk=None, mask=MASK_ALL, min_proba=0.7, out=None):
+        """B scans -> (proba [B,C] f32, label [B] i32, known [B] u8) on the device, async."""
+        self._check_cubes(cubes)
+        if self.params is None:
+            raise RadarMLError(_lib.E_NOMODEL, "no model loaded")
+        B = cubes.shape[0]
+        Cn = self.params.n_classes
+        if out is None:
+            proba = torch.empty((B, Cn), device=self.device, dtype=torch.float32)
+            label = torch.empty((B,), device=self.device, dtype=torch.int32)
+            known = torch.empty((B,), device=self.device, dtype=torch.uint8)
+        else:
+            proba, label, known = out
+        md = MODE_MAX if mode in ("max", MODE_MAX) else MODE_SLICE
+        if md == MODE_SLICE:
+            if ijk is None:
+                raise ValueError("slice mode needs ijk [B,3] int32")
+            ijk = ijk.to(device=self.device, dtype=torch.int32).contiguous()
+        work = self.workspace(B)
+        check(self.ctx, self.lib.rml_predict(self.ctx, _ptr(cubes), B, md, _ptr(ijk),
+                                             mask_bits(mask), float(min_proba), _ptr(work),
+                                             _ptr(proba), _ptr(label), _ptr(known), self._stream()))
+        return proba, label, known
+
+    def predict_host(self, cubes: np.ndarray, mode="max", ijk=None, mask=MASK_ALL, min_proba=0.7,
+                     out=None):
+        """Host float32 cubes [B,sx,sy,sz] in, host results out (H2D/compute/D2H overlapped)."""
+        sx, sy, sz = self.dims
+        if not (isinstance(cubes, np.ndarray) and cubes.dtype == np.float32
+                and cubes.flags.c_contiguous and cubes.shape[1:] == (sx, sy, sz)):
+            raise ValueError("cubes must be a C-contiguous float32 ndarray [B,%d,%d,%d]" % (sx, sy, sz))
+        if self.params is None:
+            raise RadarMLError(_lib.E_NOMODEL, "no model loaded")
+        B = cubes.shape[0]
+        Cn = self.params.n_classes
+        if out is None:
+            proba = np.empty((B, Cn), dtype=np.float32)
+            label = np.empty((B,), dtype=np.int32)
+            known = np.empty((B,), dtype=np.uint8)
+        else:
+            proba, label, known = out
+        md = MODE_MAX if mode in ("max", MODE_MAX) else MODE_SLICE
+        ij = None
+        if md == MODE_SLICE:
+            if ijk is None:
+                raise ValueError("slice mode needs ijk [B,3] int32")
+            ij = np.ascontiguousarray(ijk, dtype=np.int32)
+        check(self.ctx, self.lib.rml_predict_host(self.ctx, _np_ptr(cubes), B, md, _np_ptr(ij),
+                                                  mask_bits(mask), float(min_proba), _np_ptr(proba),
+                                                  _np_ptr(label), _np_ptr(known)))
+        self.check_status()
+        return proba, label, known
