@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — radar scans/sec (projection + classify) on N B200s, with roofline + CPU baseline.
+
+A "step" is one pass of the hot path (K1 projection -> K2 SVC-RBF scoring [-> label
+all-gather when N > 1]) over one batch of synthetic cubes already resident in HBM.
+  N = 1 : BASELINE.json configs[1]  — 65 536 cubes (31.47 GB), SVC-RBF 3-class
+  N > 1 : BASELINE.json configs[3]  — 131 072 cubes per GPU (1 M at N = 8), weak scaling
+Launch: ``python bench.py --gpus 1`` or, for N > 1,
+``python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1
+--master-port P bench.py --gpus N``.
+``--impl reference`` times the reference's own per-scan CPU path (oracle port driving
+scikit-learn's libsvm, all host cores) on the same workload definition.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CUBE_BYTES = 22 * 31 * 176 * 4            # 480 128 B, common.py:25-27
+ALGO_BYTES_PER_SCAN = CUBE_BYTES + 12 + 4  # + 3 fp32 probs + int32 label
+METRIC = "radar_scans_per_sec_proj_classify"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, torch copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def device_cubes(n, seed, device, chunk=1024):
+    """Integer-valued sparse-blob cubes generated ON the device: one anisotropic
+    Gaussian blob per scan, amplitude U(.5,1)*255, N(0,6) noise, rint, <13 -> 0, clip [0,255]."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n, 22, 31, 176), device=device, dtype=torch.float32)
+    gi = torch.arange(22, device=device, dtype=torch.float32).view(1, 22, 1, 1)
+    gj = torch.arange(31, device=device, dtype=torch.float32).view(1, 1, 31, 1)
+    gk = torch.arange(176, device=device, dtype=torch.float32).view(1, 1, 1, 176)
+    sig = torch.tensor([[1.6, 2.2, 5.0], [2.4, 3.4, 8.0], [3.6, 6.0, 13.0]], device=device)
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        cls = torch.randint(0, 3, (m,), device=device, generator=g)
+        u = torch.rand((m, 8), device=device, generator=g)
+        s = sig[cls] * (0.8 + 0.45 * u[:, 0:3])
+        ci = (2 + u[:, 3] * 17).view(m, 1, 1, 1)
+        cj = (3 + u[:, 4] * 24).view(m, 1, 1, 1)
+        ck = (10 + u[:, 5] * 155).view(m, 1, 1, 1)
+        amp = ((0.5 + 0.5 * u[:, 6]) * 255.0).view(m, 1, 1, 1)
+        v = amp * torch.exp(-0.5 * (((gi - ci) / s[:, 0].view(m, 1, 1, 1)) ** 2
+                                    + ((gj - cj) / s[:, 1].view(m, 1, 1, 1)) ** 2
+                                    + ((gk - ck) / s[:, 2].view(m, 1, 1, 1)) ** 2))
+        v += 6.0 * torch.randn(v.shape, device=device, generator=g)
+        v = torch.round(v)
+        v[v < 13.0] = 0.0
+        out[lo:lo + m] = v.clamp_(0.0, 255.0)
+        del v
+    return out
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled through NVML every ~2 ms DURING the timed region
+    (the recipe's nvidia-smi line needs >= 100 ms per sample; a timed region here is ~50 ms)."""
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+            0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        import threading
+        self.sm, self.reasons, self.power = [], set(), []
+        self.max = None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        except Exception as e:  # pragma: no cover
+            log("[bench] NVML unavailable: %r" % (e,))
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max, "reasons": sorted(self.reasons),
+               "samples": len(self.sm)}
+        if self.sm:
+            out["sm_mhz"] = float(np.median(self.sm))
+        if self.power:
+            out["power_w_max"] = float(max(self.power))
+        return out
+
+
+def build_model(seed=1234):
+    """SVC-RBF C=10 gamma=0.01 (train_svc.log:24-31) on the reference's split sizes
+    (909 train / 114 val, train_svc.log:11-13), synthetic MAX-projection features."""
+    from oracle import synth
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return synth.standard_model(seed=seed, mode="max")
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_baseline, synth
+    cores = cpu_baseline.host_cores()
+    per_gpu = args.scans_per_gpu or (65536 if args.gpus == 1 else 131072)
+    sample = int(min(4096, max(256, 32 * cores)))
+    log("[reference] fitting model, generating %d sample scans on the host" % sample)
+    cal = build_model()
+    cubes, _, _ = synth.make_cubes(sample, seed=4321)
+    classes = synth.CLASSES
+    for _ in range(args.warmup):
+        cpu_baseline.run_all_cores(cubes[: max(cores, 8)], cal, classes, cores=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_baseline.run_all_cores(cubes, cal, classes, cores=cores)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "scans/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "predict.py per-scan loop (MAX projections + process_samples + "
+                               "CalibratedClassifierCV(SVC-RBF).predict_proba), all host cores",
+                   "scans_per_gpu": per_gpu, "sample_scans_per_step": sample,
+                   "n_sv": int(cal.calibrated_classifiers_[0].estimator.estimator.support_vectors_.shape[0])},
+        "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": "port",
+                         "sample": "%d scans/step, one worker process per core, sklearn libsvm" % sample},
+        "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import cpu_baseline, restate, synth
+    from radar_ml_b200.engine import Engine
+    from radar_ml_b200.model import from_sklearn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.scans_per_gpu or (65536 if world == 1 else 131072)
+    cal = build_model()
+    params = from_sklearn(cal)
+    eng = Engine(local)
+    eng.load_model(params)
+    assert eng.model_is_integral, "bench model must take the u8 tensor-core path"
+    if rank == 0:
+        log("[bench] model n_sv=%d; generating %d cubes (%.2f GB) per GPU" % (params.n_sv, B, B * CUBE_BYTES / 1e9))
+    cubes = device_cubes(B, 1234 + rank, dev)
+    stride = eng.feature_stride(7, 1)
+    feats = torch.empty((B, stride), device=dev, dtype=torch.uint8)
+    norms = torch.empty((B,), device=dev, dtype=torch.int32)
+    C = params.n_classes
+    proba = torch.empty((B, C), device=dev, dtype=torch.float32)
+    label = torch.empty((B,), device=dev, dtype=torch.int32)
+    known = torch.empty((B,), device=dev, dtype=torch.uint8)
+    gathered = torch.empty((world * B,), device=dev, dtype=torch.int32) if world > 1 else None
+    stream = torch.cuda.current_stream(dev)
+
+    import ctypes as Ct
+    lib, ctx = eng.lib, eng.ctx
+    sp = Ct.c_void_p(stream.cuda_stream)
+
+    def step(ev=None):
+        # the two launches rml_predict makes, issued separately so K1 can be timed alone
+        if ev:
+            ev[0].record(stream)
+        rc = lib.rml_project(ctx, Ct.c_void_p(cubes.data_ptr()), B, 0, None, 7, 1,
+                             Ct.c_void_p(feats.data_ptr()), Ct.c_void_p(norms.data_ptr()), sp)
+        assert rc == 0, lib.rml_last_error(ctx)
+        if ev:
+            ev[1].record(stream)
+        rc = lib.rml_score(ctx, Ct.c_void_p(feats.data_ptr()), 1, Ct.c_void_p(norms.data_ptr()), B,
+                           0.7, Ct.c_void_p(proba.data_ptr()), None, Ct.c_void_p(label.data_ptr()),
+                           Ct.c_void_p(known.data_ptr()), sp)
+        assert rc == 0, lib.rml_last_error(ctx)
+        if ev:
+            ev[2].record(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, label)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    eng.check_status()
+    barrier()
+
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = eng.launch_count
+    barrier()
+    e0.record(stream)
+    for s in range(args.steps):
+        step(evs[s])
+    e1.record(stream)
+    barrier()
+    launches = eng.launch_count - launches0 + (args.steps if world > 1 else 0)
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    k1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    k2_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    if world > 1:
+        t = torch.tensor([ms, k1_ms, k2_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, k1_ms, k2_ms = (float(x) for x in t.cpu())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    if args.skip_extras:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world,
+                              "ms_per_step": ms / args.steps, "k1_ms": k1_ms, "k2_ms": k2_ms,
+                              "note": "--skip-extras profiling run, not a bench line"}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- e2e: host buffers through the public C-ABI call, H2D + D2H inside the timed region
+    Be = min(args.e2e_scans, B)
+    host = torch.empty((Be, 22, 31, 176), dtype=torch.float32, pin_memory=True)
+    host.copy_(cubes[:Be])
+    torch.cuda.synchronize(dev)
+    host_np = host.numpy()
+    out = (np.empty((Be, C), np.float32), np.empty((Be,), np.int32), np.empty((Be,), np.uint8))
+    for _ in range(2):
+        eng.predict_host(host_np, mode="max", out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.predict_host(host_np, mode="max", out=out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.cpu()[0])
+    e2e_value = world * Be * args.steps / e2e_s
+    e2e_labels = out[1].copy()
+
+    # ---- parity of a seeded subset against the oracle (not timed)
+    parity = None
+    cpu = None
+    if rank == 0:
+        n_par = 192
+        sub = cubes[:n_par].cpu().numpy()
+        p = restate.export_params(cal)
+        _, lab_o, _, known_o, P_o = restate.scan_path(sub, p, mode="max")
+        lab_g = label[:n_par].cpu().numpy()
+        parity = {"scans": n_par,
+                  "labels_equal": bool(np.array_equal(lab_g, lab_o)),
+                  "known_equal": bool(np.array_equal(known[:n_par].cpu().numpy().astype(bool), known_o)),
+                  "max_abs_dproba": float(np.abs(proba[:n_par].cpu().numpy().astype(np.float64) - P_o).max()),
+                  "e2e_labels_equal": bool(np.array_equal(e2e_labels[:n_par], lab_o))}
+        if world == 1:
+            cores = cpu_baseline.host_cores()
+            sample = int(min(Be, 4096, max(256, 32 * cores)))
+            v, dt, used = cpu_baseline.run_all_cores(host_np[:sample], cal, synth.CLASSES, cores=cores)
+            cpu = {"value": v, "unit": "scans/s", "cores": used, "kind": "port",
+                   "sample": "%d of the GPU-scored scans, per-scan predict.py loop, one process per "
+                             "core, sklearn libsvm (%.1f s)" % (sample, dt)}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        k1_gbs = B * CUBE_BYTES / (k1_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": ("configs[1]: batch=65536 cubes 22x31x176 fp32, SVC-RBF 3-class, MAX projections"
+                                    if world == 1 else
+                                    "configs[3]: %d cubes/GPU sharded over %d GPUs, SVC-RBF, all-gather of labels" % (B, world)),
+                       "scans_per_gpu": B, "global_batch": world * B, "n_sv": params.n_sv,
+                       "features": params.n_features, "parallelism": "dp%d" % world,
+                       "l2": "inputs (%.1f GB/GPU) larger than L2, no flush needed" % (B * CUBE_BYTES / 1e9),
+                       "e2e_scans_per_step": Be},
+            "roofline": {"bound": "hbm", "kernel": "k1_project_max<u8>", "achieved": k1_gbs, "peak": peak,
+                         "unit": "GB/s", "frac": k1_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_scan": CUBE_BYTES, "k1_ms": k1_ms, "k2_ms": k2_ms,
+                         "path_frac": (value / world) * ALGO_BYTES_PER_SCAN / (peak * 1e9)},
+            "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": Be * CUBE_BYTES,
+                    "d2h_bytes_per_step": Be * (4 * C + 4 + 1)},
+            "gpu_launches": int(launches),
+            "clocks": clocks, "parity": parity,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scans-per-gpu", type=int, default=0)
+    ap.add_argument("--e2e-scans", type=int, default=4096)
+    ap.add_argument("--skip-extras", action="store_true",
+                    help="profiling aid: skip the e2e, parity and cpu_baseline legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -91,7 +91,13 @@ def build_svc(X_train, y_train, X_val, y_val, C=10.0, gamma=0.01):
 
 
 def build_linear(X_train, y_train, X_val, y_val):
-    """train.py:368-372 SGDClassifier(loss='log') in the >=1.3 spelling + calibration."""
+    """train.py:368-372 SGDClassifier(loss='log') in the >=1.3 spelling + calibration.
+
+    scikit-learn 0.24 (requirements.txt:57) converts X to float64 inside SGD fit/predict;
+    1.9 keeps float32 end to end, which changes the arithmetic.  Fitting and calibrating on
+    float64 copies reproduces the pinned version's float64 chain."""
+    X_train = np.asarray(X_train, dtype=np.float64)
+    X_val = np.asarray(X_val, dtype=np.float64)
     from sklearn import linear_model
     from sklearn.calibration import CalibratedClassifierCV
     from sklearn.frozen import FrozenEstimator

@@ -28,7 +28,7 @@ constexpr int kK2Threads = 192;
 constexpr int kK2BlockM = 128;
 constexpr int kK2BlockKBytes = 128;          // one 128-byte swizzle span of u8 features
 constexpr int kK2MaxTileN = 256;             // columns per accumulator buffer
-constexpr int kK2Stages = 4;
+constexpr int kK2MaxStages = 8;
 constexpr int kMaxClasses = 8;
 
 struct K2Params {
@@ -37,6 +37,7 @@ struct K2Params {
   int n_tile;     // support vectors per chunk (multiple of 16, <= 256)
   int n_chunks;
   int k_blocks;   // padded feature bytes / 128
+  int stages;     // smem ring depth (host picks the deepest that fits 227 KB)
   const int32_t* unorm;    // [B]    sum u^2
   const int32_t* svnorm;   // [n_sv] sum s^2
   const double* coef;      // [C-1][n_sv]  SVC._dual_coef_
@@ -55,8 +56,12 @@ struct K2Params {
 __host__ __device__ constexpr int k2_stage_bytes(int n_tile) {
   return kK2BlockM * kK2BlockKBytes + n_tile * kK2BlockKBytes;
 }
-__host__ __device__ constexpr int k2_smem_bytes(int n_tile) {
-  return kK2Stages * k2_stage_bytes(n_tile) + 1024 /*align slack*/ + 256 /*barriers*/;
+__host__ __device__ constexpr int k2_smem_bytes(int n_tile, int stages) {
+  return stages * k2_stage_bytes(n_tile) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+inline int k2_pick_stages(int n_tile) {
+  int s = (232448 - 1024 - 256) / k2_stage_bytes(n_tile);
+  return s > kK2MaxStages ? kK2MaxStages : s;
 }
 
 // scipy.special.expit in float64
@@ -140,10 +145,11 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int stage_bytes = k2_stage_bytes(p.n_tile);
+  const int kK2Stages = p.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kK2Stages * stage_bytes);
-  uint64_t* full = bars;                    // [kK2Stages]
-  uint64_t* empty = bars + kK2Stages;       // [kK2Stages]
-  uint64_t* tfull = empty + kK2Stages;      // [2]
+  uint64_t* full = bars;                    // [stages]
+  uint64_t* empty = bars + kK2MaxStages;    // [stages]
+  uint64_t* tfull = empty + kK2MaxStages;   // [2]
   uint64_t* tempty = tfull + 2;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -173,7 +179,8 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const uint64_t pol_a = policy_evict_first();
+      // the feature tile is re-read once per support-vector chunk: keep it in L2 until then
+      const uint64_t pol_a = p.n_chunks > 1 ? policy_evict_last() : policy_evict_first();
       const uint64_t pol_b = policy_evict_last();
       uint32_t kit = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {

@@ -151,7 +151,7 @@ int encode_u8_map(rml_ctx* c, CUtensorMap* map, const void* base, int64_t rows, 
 
 template <int C>
 int launch_rbf_i8(rml_ctx* c, const CUtensorMap& map_feats, const K2Params& p, cudaStream_t st) {
-  const int smem = k2_smem_bytes(p.n_tile);
+  const int smem = k2_smem_bytes(p.n_tile, p.stages);
   RML_CUDA(c, cudaFuncSetAttribute(k2_rbf_i8<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int64_t tiles = (p.B + kK2BlockM - 1) / kK2BlockM;
   const int grid = static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
@@ -259,6 +259,7 @@ int score_impl(rml_ctx* c, const void* feats, int dtype, const int32_t* norms, i
     if (rc) return rc;
     K2Params p;
     p.B = B; p.n_sv = m.n_sv; p.n_tile = m.n_tile; p.n_chunks = m.n_chunks; p.k_blocks = m.kpad / 128;
+    p.stages = k2_pick_stages(m.n_tile);
     p.unorm = norms; p.svnorm = m.svnorm; p.coef = m.coef; p.rho = m.rho;
     p.platt_a = m.platt_a; p.platt_b = m.platt_b;
     p.neg_gamma_s2 = -m.gamma / (m.feature_scale * m.feature_scale);

@@ -139,3 +139,241 @@ def test_predict_pipeline_and_host_entry(eng, small_problem):
     ph, lh, kh = eng.predict_host(np.ascontiguousarray(cubes), mode="max")
     assert np.array_equal(lh, lab_o) and np.array_equal(kh.astype(bool), known_o)
     assert np.array_equal(ph, proba.cpu().numpy())
+
+
+# --------------------------------------------------------------------------- golden fixtures
+import os  # noqa: E402
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _golden_model(z, prefix="m_"):
+    from radar_ml_b200.model import ModelParams
+    sv = (z[prefix + "sv_u8"].astype(np.float32) / np.float32(255)).astype(np.float64)
+    return ModelParams(kind="svc_rbf", n_classes=int(z[prefix + "n_classes"]),
+                       n_features=sv.shape[1], classes=np.arange(int(z[prefix + "n_classes"])),
+                       platt_a=z[prefix + "platt_a"], platt_b=z[prefix + "platt_b"],
+                       gamma=float(z[prefix + "gamma"]), sv=sv, dual_coef=z[prefix + "dual_coef"],
+                       rho=z[prefix + "rho"], n_support=z[prefix + "n_support"])
+
+
+@pytest.mark.parametrize("mode", ["max", "slice"])
+def test_golden_reference_outputs(eng, mode):
+    """CUDA path vs outputs of the UNMODIFIED reference (tests/golden/make_golden.py)."""
+    import torch
+    z = np.load(os.path.join(G, "svc_%s.npz" % mode))
+    eng.load_model(_golden_model(z))
+    cubes = torch.from_numpy(z["cubes_u8"].astype(np.float32)).cuda()
+    ijk = torch.from_numpy(z["ijk"]).cuda()
+    feats = eng.project(cubes, mode=mode, ijk=ijk).cpu().numpy()
+    assert np.array_equal(feats, z["ref_features"])                    # process_samples, bit-exact
+    proba, label, known = eng.predict(cubes, mode=mode, ijk=ijk, min_proba=0.7)
+    eng.check_status()
+    P = proba.cpu().numpy().astype(np.float64)
+    assert np.abs(P - z["sk_predict_proba"]).max() < PROBA_TOL
+    names = np.where(known.cpu().numpy().astype(bool), z["classes"][label.cpu().numpy()], "Unknown")
+    assert list(names) == list(z["ref_names"])                         # predict.classifier names
+    best = P[np.arange(len(P)), label.cpu().numpy()]
+    assert np.abs(best - z["ref_proba"]).max() < PROBA_TOL
+
+
+def test_golden_real_sensor_xy_only(eng):
+    """491 real xy projections from ground_truth_samples.log, ProjMask(False, False, True)."""
+    import torch
+    z = np.load(os.path.join(G, "real_xy.npz"))
+    eng.load_model(_golden_model(z))
+    xy = torch.from_numpy(z["xy_u8"][z["test_idx"]].astype(np.float32)).cuda()
+    feats = eng.process_samples(None, None, xy, mask=(False, False, True), scale=True)
+    assert np.array_equal(feats.cpu().numpy(), z["ref_features_test"])
+    q, norms = eng.quantize(feats)
+    eng.check_status()
+    assert q.shape[1] == 768
+    proba, label, known = eng.score(q, norms, 0.7)
+    P = proba.cpu().numpy().astype(np.float64)
+    assert np.abs(P - z["sk_predict_proba"]).max() < PROBA_TOL
+    names = np.where(known.cpu().numpy(), z["classes"][label.cpu().numpy()], "Unknown")
+    assert list(names) == list(z["ref_names"])
+    # same thing through the general-precision kernel
+    proba2, label2, _ = eng.score(feats, None, 0.7)
+    assert np.array_equal(label2.cpu().numpy(), label.cpu().numpy())
+    assert np.abs(proba2.cpu().numpy() - proba.cpu().numpy()).max() < PROBA_TOL
+
+
+def test_golden_generated_nonintegral_process_samples(eng):
+    import torch
+    z = np.load(os.path.join(G, "generated.npz"))
+    xz, yz, xy = (torch.from_numpy(z[k]).cuda() for k in ("xz", "yz", "xy"))
+    for tag, mask in (("all", (True, True, True)), ("xz_xy", (True, False, True)), ("yz", (False, True, False))):
+        for sc in (0, 1):
+            got = eng.process_samples(xz if mask[0] else None, yz if mask[1] else None,
+                                      xy if mask[2] else None, mask=mask, scale=bool(sc))
+            assert np.array_equal(got.cpu().numpy(), z["feat_%s_%d" % (tag, sc)])
+
+
+def test_golden_matrix_indices(eng):
+    import torch
+    z = np.load(os.path.join(G, "indices.npz"))
+    got = eng.matrix_indices(torch.from_numpy(z["xyz"]).cuda()).cpu().numpy()
+    assert np.array_equal(got, z["ijk"])
+
+
+# --------------------------------------------------------------------------- other model kinds
+def test_linear_model_matches_oracle(eng, small_problem):
+    import warnings
+    import torch
+    from oracle import restate, synth
+    from radar_ml_b200.model import from_sklearn
+    X, y = small_problem["X"], small_problem["y"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        lin = synth.build_linear(X[:300], y[:300], X[300:360], y[300:360])
+    eng.load_model(from_sklearn(lin))
+    p = restate.export_params(lin)
+    cubes = small_problem["cubes"][small_problem["test"]]
+    _, lab_o, _, known_o, P_o = restate.scan_path(cubes, p, mode="max")
+    proba, label, known = eng.predict(torch.from_numpy(cubes).cuda(), mode="max")
+    eng.check_status()
+    assert np.array_equal(label.cpu().numpy(), lab_o)
+    assert np.array_equal(known.cpu().numpy().astype(bool), known_o)
+    assert np.abs(proba.cpu().numpy().astype(np.float64) - P_o).max() < PROBA_TOL
+    # float32 feature input takes the same kernel
+    Xt = torch.from_numpy(X[small_problem["test"]]).cuda()
+    proba2, label2, _ = eng.score(Xt, None, 0.7)
+    assert np.array_equal(label2.cpu().numpy(), lab_o)
+    assert np.abs(proba2.cpu().numpy().astype(np.float64) - P_o).max() < PROBA_TOL
+
+
+def test_two_class_svc(eng):
+    import warnings
+    import torch
+    from oracle import restate, synth
+    from radar_ml_b200.model import from_sklearn
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cubes, y, _ = synth.make_cubes(220, seed=31, n_classes=2)
+        X = synth.features(*synth.project_max(cubes))
+        cal = synth.build_svc(X[:120], y[:120], X[120:160], y[120:160])
+    eng.load_model(from_sklearn(cal))
+    p = restate.export_params(cal)
+    _, lab_o, _, known_o, P_o = restate.scan_path(cubes[160:], p, mode="max")
+    proba, label, known = eng.predict(torch.from_numpy(cubes[160:]).cuda(), mode="max")
+    eng.check_status()
+    assert np.array_equal(label.cpu().numpy(), lab_o)
+    assert np.abs(proba.cpu().numpy().astype(np.float64) - P_o).max() < PROBA_TOL
+
+
+def test_many_support_vectors_multi_chunk(eng, small_problem):
+    """n_sv > 256 exercises several TMEM accumulator chunks (C=1000 keeps most points as SVs)."""
+    import warnings
+    import torch
+    from oracle import restate, synth
+    from radar_ml_b200.model import from_sklearn
+    X, y = small_problem["X"], small_problem["y"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cal = synth.build_svc(X[:340], y[:340], X[340:360], y[340:360], C=10.0, gamma=0.5)
+    p = restate.export_params(cal)
+    assert p.sv.shape[0] > 256
+    eng.load_model(from_sklearn(cal))
+    cubes = small_problem["cubes"][small_problem["test"]]
+    _, lab_o, _, known_o, P_o = restate.scan_path(cubes, p, mode="max")
+    proba, label, known = eng.predict(torch.from_numpy(cubes).cuda(), mode="max")
+    eng.check_status()
+    assert np.array_equal(label.cpu().numpy(), lab_o)
+    assert np.abs(proba.cpu().numpy().astype(np.float64) - P_o).max() < PROBA_TOL
+
+
+# --------------------------------------------------------------------------- reference-facing API
+def test_drop_in_common_and_predict_api(eng, small_problem):
+    """common.process_samples / predict.classifier called exactly like predict.py:112-119."""
+    from oracle import restate, synth
+    from radar_ml_b200 import common, predict
+    common.set_engine(eng)
+    cal = small_problem["cal"]
+    le = synth.LabelEncoderLike()
+    p = small_problem["params"]
+    cubes = small_problem["cubes"][small_problem["test"]][:12]
+    ijk = small_problem["ijk"][small_problem["test"]][:12]
+    for s in range(12):
+        raw = cubes[s]
+        i, j, k = (int(v) for v in ijk[s])
+        yz, xz, xy = raw[i, :, :], raw[:, j, :], raw[:, :, k]
+        zoom = predict.calc_proj_zoom(22, 31, 176, 22, 31, 176)
+        obs = common.process_samples([(xz, yz, xy)], proj_mask=common.ProjMask(True, True, True),
+                                     proj_zoom=zoom, scale=True)
+        want = restate.process_samples([(xz, yz, xy)], scale=True)
+        assert obs.dtype == np.float32 and np.array_equal(obs, want)
+        name, proba = predict.classifier(obs, cal, le, 0.7)       # sklearn object accepted as-is
+        name_o, proba_o = restate.classifier(obs, p, le.classes_, 0.7)
+        assert name == name_o and abs(proba - proba_o) < PROBA_TOL
+    with pytest.raises(NotImplementedError):
+        common.process_samples([(xz, yz, xy)], proj_zoom=predict.calc_proj_zoom(22, 31, 176, 11, 31, 176))
+    assert common.calculate_matrix_indices(12.5, -3.0, 140.0, 22, 31, 176) == \
+        restate.calculate_matrix_indices(12.5, -3.0, 140.0, 22, 31, 176)
+
+
+def test_predict_loop_with_recorded_radar(eng, small_problem):
+    """predict.predict (predict.py:72-131) replayed from a fake Walabot SDK object."""
+    from oracle import restate, synth
+    from radar_ml_b200 import common, predict
+    common.set_engine(eng)
+    cubes = small_problem["cubes"][small_problem["test"]][:5]
+
+    class Target:
+        def __init__(self, x, y, z):
+            self.xPosCm, self.yPosCm, self.zPosCm, self.amplitude = x, y, z, 1.0
+
+    class FakeRadar:
+        def __init__(self):
+            self.n = -1
+            self.stopped = False
+        def Trigger(self):
+            self.n += 1
+        def GetSensorTargets(self):
+            if self.n == 1:
+                return []                       # predict.py:86-87: no targets -> continue
+            return [Target(5.0 + self.n, -4.0, 120.0 + 10 * self.n), Target(-20.0, 10.0, 200.0)]
+        def GetRawImage(self):
+            return cubes[self.n].tolist(), 22, 31, 176, 0.0
+        def Stop(self):
+            self.stopped = True
+        def Disconnect(self):
+            pass
+        def Clean(self):
+            pass
+
+    radar = FakeRadar()
+    le = synth.LabelEncoderLike()
+    res = predict.predict(0.7, small_problem["cal"], le, common.ProjMask(True, True, True),
+                          radar=radar, max_scans=5)
+    assert radar.stopped and len(res) == 8
+    p = small_problem["params"]
+    want = []
+    for n in (0, 2, 3, 4):
+        for (x, y, z) in ((5.0 + n, -4.0, 120.0 + 10 * n), (-20.0, 10.0, 200.0)):
+            ijk = restate.calculate_matrix_indices(x, y, z, 22, 31, 176)
+            t = restate.project(cubes[n], "slice", ijk)
+            obs = restate.process_samples([t], scale=True)
+            want.append(restate.classifier(obs, p, le.classes_, 0.7))
+    for (n1, p1), (n2, p2) in zip(res, want):
+        assert n1 == n2 and abs(p1 - p2) < PROBA_TOL
+
+
+def test_error_paths(eng, small_problem):
+    import torch
+    from radar_ml_b200._lib import RadarMLError
+    from radar_ml_b200.model import from_sklearn
+    eng.load_model(from_sklearn(small_problem["cal"]))
+    d = torch.zeros((2, 22, 31, 176), device="cuda")
+    with pytest.raises(RadarMLError):
+        eng.predict(d, mask=(True, False, False))            # F mismatch with the model
+    with pytest.raises(ValueError):
+        eng.project(torch.zeros((2, 22, 31, 100), device="cuda"))
+    with pytest.raises(ValueError):
+        eng.project(d, mode="slice")                         # slice needs ijk
+    bad = torch.tensor([[0, 0, 176], [0, 0, 0]], dtype=torch.int32, device="cuda")
+    eng.project(d, mode="slice", ijk=bad)
+    with pytest.raises(RadarMLError):
+        eng.check_status()                                   # numpy would raise IndexError
+    empty = torch.zeros((0, 22, 31, 176), device="cuda")
+    assert eng.project(empty).shape == (0, 10010)            # empty batch is a no-op
