@@ -144,6 +144,8 @@ class Engine:
             if ijk is None:
                 raise ValueError("slice mode needs ijk [B,3] int32")
             ijk = ijk.to(device=self.device, dtype=torch.int32).contiguous()
+        if B == 0:   # empty batch: nothing to launch (zero-size tensors have no storage)
+            return (out, norms) if dtype == U8 else out
         check(self.ctx, self.lib.rml_project(self.ctx, _ptr(cubes), B, md, _ptr(ijk), m, dtype,
                                              _ptr(out), _ptr(norms), self._stream()))
         return (out, norms) if dtype == U8 else out
@@ -181,6 +183,8 @@ class Engine:
         dec = None
         if want_decision:
             dec = torch.empty((B,) if Cn == 2 else (B, Cn), device=self.device, dtype=torch.float32)
+        if B == 0:
+            return (proba, label, known.bool()) + ((dec,) if want_decision else ())
         check(self.ctx, self.lib.rml_score(self.ctx, _ptr(feats), dtype, _ptr(norms), B,
                                            float(min_proba), _ptr(proba), _ptr(dec), _ptr(label),
                                            _ptr(known), self._stream()))
@@ -241,6 +245,8 @@ class Engine:
             if ijk is None:
                 raise ValueError("slice mode needs ijk [B,3] int32")
             ijk = ijk.to(device=self.device, dtype=torch.int32).contiguous()
+        if B == 0:
+            return proba, label, known
         work = self.workspace(B)
         check(self.ctx, self.lib.rml_predict(self.ctx, _ptr(cubes), B, md, _ptr(ijk),
                                              mask_bits(mask), float(min_proba), _ptr(work),
