@@ -94,7 +94,8 @@ int rml_model_is_integral(const rml_ctx* ctx);
 int rml_project(rml_ctx* ctx, const float* cubes_dev, int64_t B, int mode, const int32_t* ijk_dev,
                 uint32_t mask, int dtype, void* feats_dev, int32_t* norms_dev, rml_stream stream);
 /* common.process_samples on already-extracted projections (common.py:123-149, zoom 1.0):
- * xz [B][sx][sz], yz [B][sy][sz], xy [B][sx][sy] float32 device arrays (NULL if masked out). */
+ * xz [B][sx][sz], yz [B][sy][sz], xy [B][sx][sy] float32 device arrays (NULL if masked out).
+ * scale != 0 applies the rml_set_affine transform (default (x-0)/255 = common.py:148). */
 int rml_process_samples(rml_ctx* ctx, const float* xz_dev, const float* yz_dev,
                         const float* xy_dev, int64_t B, uint32_t mask, int scale,
                         float* feats_dev, rml_stream stream);
@@ -131,6 +132,52 @@ int rml_predict(rml_ctx* ctx, const float* cubes_dev, int64_t B, int mode, const
 int rml_predict_host(rml_ctx* ctx, const float* cubes_host, int64_t B, int mode,
                      const int32_t* ijk_host, uint32_t mask, double min_proba, float* proba_host,
                      int32_t* label_host, uint8_t* known_host);
+
+/* ---- dnn.py / sgan.py classifier forward ------------------------ */
+/* Load sequence: begin -> resize tables x3 -> conv layers (per layer, per branch) -> dense ->
+ * finish.  All pointers are HOST pointers.  BatchNorm (sgan.py:138,144,150,190,195) is folded
+ * into the preceding kernel/bias by the caller (inference form, epsilon 1e-3); Dropout is the
+ * identity at inference.
+ *   resize_to   80 (dnn.py:33) or 128 (sgan.py:39);  head 0 = softmax (dnn.py:85, sgan c_model
+ *   sgan.py:205), 1 = Z/(Z+1), Z = sum exp(logit) (sgan d_model, sgan.py:125-129, 210-213)
+ *   act: 0 none, 1 ReLU (dnn.py:48-52), 2 LeakyReLU(alpha) (sgan.py:141) */
+int rml_net_begin(rml_ctx* ctx, int resize_to, int n_classes, int head, float lrelu_alpha);
+/* Pillow Resample.c BICUBIC coefficient tables of branch b (0 xz, 1 yz, 2 xy): kh [R][ksh]
+ * with bounds bh [R][2] = (first input column, taps) for the horizontal pass, kv/bv vertical */
+int rml_net_set_resize_tables(rml_ctx* ctx, int branch, int ksh, const double* kh_host,
+                              const int32_t* bh_host, int ksv, const double* kv_host,
+                              const int32_t* bv_host);
+/* Conv2D(cout, 3x3, strides 2, 'same') of tower `branch`, layer index from 0: kernel in Keras
+ * (kh,kw,cin,cout) order, dnn.py:45-52 / sgan.py:132-154 */
+int rml_net_add_conv(rml_ctx* ctx, int layer, int branch, int cin, int cout, int act,
+                     const float* w_hwio_host, const float* bias_host);
+/* Dense 64 -> Dense 64 -> Dense C (dnn.py:80-85, sgan.py:188-202).  w1t: bf16 bits [64][K],
+ * K ordered [branch][h][w][c] (the caller permutes Keras' Flatten order (h,w,96)); w2 [64][64]
+ * and w3 [64][C] input-major float32. */
+int rml_net_set_dense(rml_ctx* ctx, int K, const uint16_t* w1t_bf16_host, const float* b1_host,
+                      int act1, const float* w2_host, const float* b2_host, int act2,
+                      const float* w3_host, const float* b3_host);
+int rml_net_finish(rml_ctx* ctx);
+size_t rml_net_workspace_bytes(const rml_ctx* ctx, int64_t chunk_scans);
+/* feats_dev: float32 [B][10010] projections scaled (p-127.5)/127.5 (rml_project with
+ * rml_set_affine(127.5, 127.5, 1)).  The batch is processed in chunks that fit the workspace.
+ * proba_dev [B][C], logits_dev [B][C] nullable, label_dev [B]. */
+int rml_net_forward(rml_ctx* ctx, const float* feats_dev, int64_t B, void* workspace_dev,
+                    size_t workspace_bytes, float* proba_dev, float* logits_dev, int32_t* label_dev,
+                    rml_stream stream);
+/* dnn.py:240-254 alone: scaled projections -> images_dev float32 [B][3][R][R] */
+int rml_net_resize(rml_ctx* ctx, const float* feats_dev, int64_t B, float* images_dev,
+                   rml_stream stream);
+/* Keras model.predict([XZ, YZ, XY]) on preprocessed inputs images_dev [B][3][R][R].
+ * tower_bf16_dev (nullable): receives the flattened conv-tower output, bf16 bits [B][K] in
+ * [branch][h][w][c] order — the operand the tensor-core dense stack consumed. */
+int rml_net_forward_images(rml_ctx* ctx, const float* images_dev, int64_t B, void* workspace_dev,
+                           size_t workspace_bytes, float* proba_dev, float* logits_dev,
+                           int32_t* label_dev, uint16_t* tower_bf16_dev, rml_stream stream);
+/* cubes -> projections -> scale -> resize -> towers -> dense stack (configs[2], configs[4]) */
+int rml_net_predict(rml_ctx* ctx, const float* cubes_dev, int64_t B, int mode,
+                    const int32_t* ijk_dev, void* workspace_dev, size_t workspace_bytes,
+                    float* proba_dev, int32_t* label_dev, rml_stream stream);
 
 /* ---- status of the last asynchronous work (non-integral count seen by the u8 path) ----- */
 int rml_check_status(rml_ctx* ctx, rml_stream stream); /* synchronises the stream */

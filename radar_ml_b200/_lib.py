@@ -79,6 +79,16 @@ SIGNATURES = {
     "rml_predict_workspace_bytes": (_sz, [_vp, _i64]),
     "rml_predict": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _u32, _f64, _vp, _vp, _vp, _vp, _vp]),
     "rml_predict_host": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _u32, _f64, _vp, _vp, _vp]),
+    "rml_net_begin": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32]),
+    "rml_net_set_resize_tables": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp]),
+    "rml_net_add_conv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "rml_net_set_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp]),
+    "rml_net_finish": (C.c_int, [_vp]),
+    "rml_net_workspace_bytes": (_sz, [_vp, _i64]),
+    "rml_net_forward": (C.c_int, [_vp, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "rml_net_resize": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "rml_net_forward_images": (C.c_int, [_vp, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "rml_net_predict": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _sz, _vp, _vp, _vp]),
     "rml_check_status": (C.c_int, [_vp, _vp]),
     "rml_launch_count": (_i64, [_vp]),
 }

@@ -418,7 +418,7 @@ struct PsParams {
   int64_t B;
   int F;
   int scale;
-  float scale_value;
+  float offset, scale_value;   // (v - offset) / scale_value when scale != 0
 };
 __global__ void __launch_bounds__(256) k1_process_samples(const PsParams p) {
   const int64_t total = p.B * static_cast<int64_t>(p.F);
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(256) k1_process_samples(const PsParams p) {
     for (int q = 0; q < 3; ++q)
       if (p.proj[q] && f >= p.off[q] && f < p.off[q] + p.len[q])
         v = p.proj[q][b * p.len[q] + (f - p.off[q])];
-    p.feats[e] = p.scale ? __fdiv_rn(v, p.scale_value) : v;
+    p.feats[e] = p.scale ? __fdiv_rn(v - p.offset, p.scale_value) : v;
   }
 }
 

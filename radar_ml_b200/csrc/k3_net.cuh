@@ -1,0 +1,382 @@
+// K3/K4/K5 — the dnn.py / sgan.py classifier forward pass.
+//   k3_resize_pil   dnn.py:240-245 / sgan.py:676-681: PIL Image.resize((R,R), BICUBIC) of the
+//                   three projections as a fixed separable operator (Pillow Resample.c tables
+//                   computed on the host), double accumulation, float32 store — bit-exact.
+//   k4_conv3x3s2    Keras Conv2D(3x3, strides 2, 'same') + folded BatchNorm + ReLU/LeakyReLU
+//                   (dnn.py:45-52, sgan.py:132-154), NHWC, fp32 CUDA-core direct conv
+//                   (round-1 correctness-first version; tensor-core implicit GEMM is next).
+//   k5_dense_stack  Flatten -> Dense 64 -> Dense 64 -> Dense C -> softmax / Z/(Z+1)
+//                   (dnn.py:78-85, sgan.py:185-213).  The K = 38 400 / 24 576 contraction runs
+//                   on tcgen05 (kind::f16, bf16 operands, fp32 accumulate in TMEM, TMA-fed
+//                   128B-swizzled tiles); the two 64-wide layers and the head are fused into
+//                   the TMEM epilogue in fp32.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "ptx.cuh"
+
+namespace rml {
+
+// ------------------------------------------------------------------------------ K3 resize
+struct ResizeParams {
+  const float* feats;     // [B][F] projections already scaled (p-127.5)/127.5 by K1
+  float* images;          // [B][3][R][R]
+  int64_t B;
+  int F, R;
+  int ph[3], pw[3], poff[3];   // projection heights / widths / offsets inside a feature row
+  const double* kh[3];    // horizontal tables [R][ksh]   (pw -> R)
+  const double* kv[3];    // vertical tables   [R][ksv]   (ph -> R)
+  const int2* bh[3];      // [R] (first input index, taps)
+  const int2* bv[3];
+  int ksh[3], ksv[3];
+};
+
+// one CTA per (scan, branch); smem: projection + horizontal-pass result
+__global__ void __launch_bounds__(256) k3_resize_pil(const ResizeParams p) {
+  extern __shared__ float rs_smem[];
+  const int br = blockIdx.y;
+  const int H = p.ph[br], W = p.pw[br], R = p.R;
+  float* src = rs_smem;             // [H][W]
+  float* tmp = rs_smem + H * W;     // [H][R]
+  for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const float* g = p.feats + b * p.F + p.poff[br];
+    for (int e = threadIdx.x; e < H * W; e += blockDim.x) src[e] = g[e];
+    __syncthreads();
+    // horizontal pass (ImagingResampleHorizontal_32bpc): double accumulate, float store
+    const double* kh = p.kh[br];
+    const int2* bh = p.bh[br];
+    const int ksh = p.ksh[br];
+    for (int e = threadIdx.x; e < H * R; e += blockDim.x) {
+      const int y = e / R, xx = e - y * R;
+      const int2 bd = bh[xx];
+      double ss = 0.0;
+      for (int x = 0; x < bd.y; ++x) ss += static_cast<double>(src[y * W + bd.x + x]) * kh[xx * ksh + x];
+      tmp[e] = static_cast<float>(ss);
+    }
+    __syncthreads();
+    const double* kv = p.kv[br];
+    const int2* bv = p.bv[br];
+    const int ksv = p.ksv[br];
+    float* out = p.images + (b * 3 + br) * static_cast<int64_t>(R) * R;
+    for (int e = threadIdx.x; e < R * R; e += blockDim.x) {
+      const int yy = e / R, xx = e - yy * R;
+      const int2 bd = bv[yy];
+      double ss = 0.0;
+      for (int y = 0; y < bd.y; ++y) ss += static_cast<double>(tmp[(bd.x + y) * R + xx]) * kv[yy * ksv + y];
+      out[e] = static_cast<float>(ss);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------ K4 conv
+constexpr int kConvCoutTile = 32;
+struct ConvParams {
+  const float* in;        // [n_img][H][W][Cin]   (n_img = scans * 3, branch = img % 3)
+  void* out;              // [n_img][Ho][Wo][Cout] fp32 or bf16
+  const float* w[3];      // per branch [3][3][Cin][Cout] (Keras HWIO, BN folded)
+  const float* bias[3];   // per branch [Cout]
+  int64_t n_img;
+  int H, W, Cin, Cout, Ho, Wo, pad_t, pad_l;
+  int act;                // 0 none, 1 relu, 2 leaky relu
+  float alpha;
+  int out_bf16;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float alpha) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return v >= 0.f ? v : alpha * v;
+  return v;
+}
+
+// grid: (pixel blocks, Cout/32, 3 branches); each thread = one output pixel x 32 channels;
+// the 9*Cin*32 weights of this (branch, channel group) live in shared memory.
+__global__ void __launch_bounds__(256) k4_conv3x3s2(const ConvParams p) {
+  extern __shared__ float cw[];   // [9][Cin][32]
+  const int br = blockIdx.z;
+  const int cg = blockIdx.y;
+  const float* wsrc = p.w[br];
+  const int n_w = 9 * p.Cin * kConvCoutTile;
+  for (int e = threadIdx.x; e < n_w; e += blockDim.x) {
+    const int co = e % kConvCoutTile;
+    const int t = e / kConvCoutTile;          // tap * Cin + ci
+    cw[e] = wsrc[t * p.Cout + cg * kConvCoutTile + co];
+  }
+  __syncthreads();
+  const int64_t per_branch = (p.n_img / 3) * p.Ho * p.Wo;
+  const float* bias = p.bias[br] + cg * kConvCoutTile;
+  for (int64_t pix = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; pix < per_branch;
+       pix += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(pix % p.Wo);
+    const int oy = static_cast<int>((pix / p.Wo) % p.Ho);
+    const int64_t scan = pix / (static_cast<int64_t>(p.Wo) * p.Ho);
+    const int64_t img = scan * 3 + br;
+    float acc[kConvCoutTile];
+#pragma unroll
+    for (int c = 0; c < kConvCoutTile; ++c) acc[c] = bias[c];
+    for (int kh = 0; kh < 3; ++kh) {
+      const int iy = oy * 2 + kh - p.pad_t;
+      if (iy < 0 || iy >= p.H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ix = ox * 2 + kw - p.pad_l;
+        if (ix < 0 || ix >= p.W) continue;
+        const float* xin = p.in + ((img * p.H + iy) * p.W + ix) * p.Cin;
+        const float* wt = cw + (kh * 3 + kw) * p.Cin * kConvCoutTile;
+        if ((p.Cin & 3) == 0) {
+          for (int ci = 0; ci < p.Cin; ci += 4) {
+            const float4 xv = *reinterpret_cast<const float4*>(xin + ci);
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4* w4 = reinterpret_cast<const float4*>(wt + (ci + u) * kConvCoutTile);
+#pragma unroll
+              for (int c4 = 0; c4 < kConvCoutTile / 4; ++c4) {
+                const float4 wv = w4[c4];
+                acc[c4 * 4 + 0] = fmaf(xs[u], wv.x, acc[c4 * 4 + 0]);
+                acc[c4 * 4 + 1] = fmaf(xs[u], wv.y, acc[c4 * 4 + 1]);
+                acc[c4 * 4 + 2] = fmaf(xs[u], wv.z, acc[c4 * 4 + 2]);
+                acc[c4 * 4 + 3] = fmaf(xs[u], wv.w, acc[c4 * 4 + 3]);
+              }
+            }
+          }
+        } else {
+          for (int ci = 0; ci < p.Cin; ++ci) {
+            const float x = xin[ci];
+#pragma unroll
+            for (int c = 0; c < kConvCoutTile; ++c) acc[c] = fmaf(x, wt[ci * kConvCoutTile + c], acc[c]);
+          }
+        }
+      }
+    }
+    const int64_t o = ((img * p.Ho + oy) * p.Wo + ox) * p.Cout + cg * kConvCoutTile;
+    if (p.out_bf16) {
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + o;
+#pragma unroll
+      for (int c = 0; c < kConvCoutTile; c += 2)
+        *reinterpret_cast<__nv_bfloat162*>(out + c) =
+            __floats2bfloat162_rn(apply_act(acc[c], p.act, p.alpha), apply_act(acc[c + 1], p.act, p.alpha));
+    } else {
+      float* out = reinterpret_cast<float*>(p.out) + o;
+#pragma unroll
+      for (int c = 0; c < kConvCoutTile; c += 4)
+        *reinterpret_cast<float4*>(out + c) =
+            make_float4(apply_act(acc[c], p.act, p.alpha), apply_act(acc[c + 1], p.act, p.alpha),
+                        apply_act(acc[c + 2], p.act, p.alpha), apply_act(acc[c + 3], p.act, p.alpha));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ K5 dense stack
+constexpr int kK5Threads = 192;
+constexpr int kK5BlockM = 128;
+constexpr int kK5N = 64;
+constexpr int kK5BlockK = 64;        // bf16 elements = one 128-byte swizzle span
+constexpr int kK5Stages = 8;
+constexpr int kK5StageBytes = (kK5BlockM + kK5N) * kK5BlockK * 2;   // 24 576
+
+struct K5Params {
+  int64_t B;
+  int k_blocks;           // K / 64
+  int C;                  // classes
+  int head;               // 0 softmax (dnn, sgan c_model), 1 Z/(Z+1) (sgan d_model)
+  int act1, act2;
+  float alpha;
+  const float* b1;        // [64]  (BN folded)
+  const float* w2;        // [64][64] in-major
+  const float* b2;
+  const float* w3;        // [64][C]
+  const float* b3;
+  float* proba;           // [B][C]
+  float* logits;          // [B][C], nullable
+  int32_t* label;         // [B]
+};
+
+__host__ __device__ constexpr int k5_smem_bytes() {
+  return kK5Stages * kK5StageBytes + 1024 + 256 + (64 * 64 + 64 * 8 + 64 * 2 + 8) * 4;
+}
+
+__global__ void __launch_bounds__(kK5Threads, 1)
+k5_dense_stack(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w1,
+               const K5Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kK5Stages * kK5StageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kK5Stages;
+  uint64_t* tfull = empty + kK5Stages;     // [2]
+  uint64_t* tempty = tfull + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_w2 = reinterpret_cast<float*>(smem + kK5Stages * kK5StageBytes + 256);
+  float* s_w3 = s_w2 + 64 * 64;            // [64][8]
+  float* s_b1 = s_w3 + 64 * 8;
+  float* s_b2 = s_b1 + 64;
+  float* s_b3 = s_b2 + 64;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_tiles = (p.B + kK5BlockM - 1) / kK5BlockM;
+
+  for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) s_w2[e] = p.w2[e];
+  for (int e = threadIdx.x; e < 64 * 8; e += blockDim.x) {
+    const int i = e >> 3, c = e & 7;
+    s_w3[e] = c < p.C ? p.w3[i * p.C + c] : 0.f;
+  }
+  if (threadIdx.x < 64) {
+    s_b1[threadIdx.x] = p.b1[threadIdx.x];
+    s_b2[threadIdx.x] = p.b2[threadIdx.x];
+  }
+  if (threadIdx.x < 8) s_b3[threadIdx.x] = threadIdx.x < p.C ? p.b3[threadIdx.x] : 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kK5Stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_act);
+    tma_prefetch_desc(&map_w1);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol_a = policy_evict_first();
+      const uint64_t pol_b = policy_evict_last();
+      uint32_t kit = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
+          const int s = kit % kK5Stages;
+          mbar_wait(&empty[s], ((kit / kK5Stages) & 1) ^ 1);
+          unsigned char* a_dst = smem + s * kK5StageBytes;
+          unsigned char* b_dst = a_dst + kK5BlockM * kK5BlockK * 2;
+          mbar_arrive_expect_tx(&full[s], kK5StageBytes);
+          tma_load_2d(a_dst, &map_act, kb * kK5BlockK, static_cast<int32_t>(tile * kK5BlockM), &full[s], pol_a);
+          tma_load_2d(b_dst, &map_w1, kb * kK5BlockK, 0, &full[s], pol_b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(kCF32, kFmtBF16, kFmtBF16, kK5BlockM, kK5N);
+      uint32_t kit = 0, ait = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ait) {
+        const int ab = ait & 1;
+        mbar_wait(&tempty[ab], ((ait >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * kK5N;
+        for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
+          const int s = kit % kK5Stages;
+          mbar_wait(&full[s], (kit / kK5Stages) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * kK5StageBytes);
+          const uint32_t b_addr = a_addr + kK5BlockM * kK5BlockK * 2;
+          const uint64_t da = umma_desc_k_sw128(a_addr);
+          const uint64_t db = umma_desc_k_sw128(b_addr);
+#pragma unroll
+          for (int ks = 0; ks < kK5BlockK / 16; ++ks)   // UMMA_K = 16 bf16 = 32 bytes
+            umma_f16(d_tmem, da + (ks * 32 >> 4), db + (ks * 32 >> 4), idesc, (kb | ks) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[ab]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    uint32_t ait = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ait) {
+      const int ab = ait & 1;
+      const int64_t b = tile * kK5BlockM + m;
+      mbar_wait(&tfull[ab], (ait >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ab * kK5N + (static_cast<uint32_t>(q * 32) << 16);
+      float h1[64];
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(taddr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          h1[c0 + e] = apply_act(__uint_as_float(v[e]) + s_b1[c0 + e], p.act1, p.alpha);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[ab]);
+      if (b < p.B) {
+        float h2[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) h2[j] = s_b2[j];
+#pragma unroll 4
+        for (int i = 0; i < 64; ++i) {
+          const float x = h1[i];
+          const float4* w4 = reinterpret_cast<const float4*>(s_w2 + i * 64);
+#pragma unroll
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const float4 wv = w4[j4];
+            h2[j4 * 4 + 0] = fmaf(x, wv.x, h2[j4 * 4 + 0]);
+            h2[j4 * 4 + 1] = fmaf(x, wv.y, h2[j4 * 4 + 1]);
+            h2[j4 * 4 + 2] = fmaf(x, wv.z, h2[j4 * 4 + 2]);
+            h2[j4 * 4 + 3] = fmaf(x, wv.w, h2[j4 * 4 + 3]);
+          }
+        }
+        float lg[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) lg[c] = s_b3[c];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const float x = apply_act(h2[i], p.act2, p.alpha);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) lg[c] = fmaf(x, s_w3[i * 8 + c], lg[c]);
+        }
+        int best = 0;
+        float mx = lg[0];
+#pragma unroll
+        for (int c = 1; c < 8; ++c)
+          if (c < p.C && lg[c] > mx) { mx = lg[c]; best = c; }
+        if (p.head == 0) {
+          double e[8], den = 0.0;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            e[c] = c < p.C ? exp(static_cast<double>(lg[c]) - static_cast<double>(mx)) : 0.0;
+            den += e[c];
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < p.C) p.proba[b * p.C + c] = static_cast<float>(e[c] / den);
+          p.label[b] = best;
+        } else {
+          double z = 0.0;   // sgan.py:125-129 custom_activation
+#pragma unroll
+          for (int c = 0; c < 8; ++c) z += c < p.C ? exp(static_cast<double>(lg[c])) : 0.0;
+          const double d = z / (z + 1.0);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < p.C) p.proba[b * p.C + c] = c == 0 ? static_cast<float>(d) : 0.f;
+          p.label[b] = d >= 0.5 ? 1 : 0;
+        }
+        if (p.logits) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < p.C) p.logits[b * p.C + c] = lg[c];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace rml

@@ -15,6 +15,7 @@
 
 #include "k1_project.cuh"
 #include "k2_score.cuh"
+#include "k3_net.cuh"
 
 using namespace rml;
 
@@ -53,6 +54,27 @@ struct HostPipe {
   size_t work_bytes = 0;
 };
 
+struct NetConv {
+  int cin = 0, cout = 0, act = 0;
+  float* w[3] = {nullptr, nullptr, nullptr};
+  float* bias[3] = {nullptr, nullptr, nullptr};
+};
+struct Net {
+  bool ready = false;
+  int R = 0, C = 0, head = 0;
+  float alpha = 0.2f;
+  std::vector<NetConv> convs;
+  int K = 0, act1 = 0, act2 = 0;
+  uint16_t* w1t = nullptr;  // bf16 [64][K]
+  float *b1 = nullptr, *w2 = nullptr, *b2 = nullptr, *w3 = nullptr, *b3 = nullptr;
+  double* kh[3] = {nullptr, nullptr, nullptr};
+  double* kv[3] = {nullptr, nullptr, nullptr};
+  int2* bh[3] = {nullptr, nullptr, nullptr};
+  int2* bv[3] = {nullptr, nullptr, nullptr};
+  int ksh[3] = {0, 0, 0}, ksv[3] = {0, 0, 0};
+  CUtensorMap map_w1;
+};
+
 }  // namespace
 
 struct rml_ctx {
@@ -68,6 +90,7 @@ struct rml_ctx {
   std::string err;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   HostPipe pipe;
+  Net net;
 };
 
 namespace {
@@ -304,6 +327,14 @@ int predict_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
   return score_impl(c, work, dtype, norms, B, min_proba, proba, nullptr, label, known, st);
 }
 
+void free_net(Net& n) {
+  for (auto& cv : n.convs)
+    for (int b = 0; b < 3; ++b) { cudaFree(cv.w[b]); cudaFree(cv.bias[b]); }
+  cudaFree(n.w1t); cudaFree(n.b1); cudaFree(n.w2); cudaFree(n.b2); cudaFree(n.w3); cudaFree(n.b3);
+  for (int b = 0; b < 3; ++b) { cudaFree(n.kh[b]); cudaFree(n.kv[b]); cudaFree(n.bh[b]); cudaFree(n.bv[b]); }
+  n = Net();
+}
+
 void free_pipe(HostPipe& hp) {
   for (int i = 0; i < kHostBufs; ++i) {
     cudaFree(hp.cubes[i]); cudaFree(hp.ijk[i]); cudaFree(hp.work[i]);
@@ -366,6 +397,7 @@ int rml_destroy(rml_ctx* c) {
   cudaDeviceSynchronize();
   free_model(c->model);
   free_pipe(c->pipe);
+  free_net(c->net);
   cudaFree(c->status);
   delete c;
   return RML_OK;
@@ -498,7 +530,9 @@ int rml_process_samples(rml_ctx* c, const float* xz, const float* yz, const floa
   p.off[0] = 0;
   p.off[1] = (mask & 1) ? p.len[0] : 0;
   p.off[2] = p.off[1] + ((mask & 2) ? p.len[1] : 0);
-  p.feats = feats; p.B = B; p.F = feature_len(c, mask); p.scale = scale; p.scale_value = 255.f;
+  p.feats = feats; p.B = B; p.F = feature_len(c, mask); p.scale = scale;
+  // scale != 0 applies the context affine: default (0, 255) = common.py:148; (127.5, 127.5) = dnn.py:203
+  p.offset = c->aff_offset; p.scale_value = c->aff_scale;
   const int64_t total = B * p.F;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 16ll * c->num_sms) blocks = 16ll * c->num_sms;
@@ -631,5 +665,322 @@ int rml_check_status(rml_ctx* c, rml_stream stream) {
 }
 
 int64_t rml_launch_count(const rml_ctx* c) { return c ? c->launches : 0; }
+
+
+// ------------------------------------------------------------------------------ networks
+int rml_net_begin(rml_ctx* c, int resize_to, int n_classes, int head, float alpha) {
+  if (!c) return RML_E_INVALID;
+  if (resize_to < 8 || resize_to > 256 || n_classes < 1 || n_classes > 8 || head < 0 || head > 1)
+    return fail(c, RML_E_INVALID, "rml_net_begin: bad arguments");
+  DeviceGuard g(c->device);
+  cudaDeviceSynchronize();
+  free_net(c->net);
+  c->net.R = resize_to; c->net.C = n_classes; c->net.head = head; c->net.alpha = alpha;
+  return RML_OK;
+}
+
+int rml_net_set_resize_tables(rml_ctx* c, int branch, int ksh, const double* kh, const int32_t* bh,
+                              int ksv, const double* kv, const int32_t* bv) {
+  if (!c) return RML_E_INVALID;
+  Net& n = c->net;
+  if (branch < 0 || branch > 2 || n.R == 0 || !kh || !bh || !kv || !bv || ksh <= 0 || ksv <= 0)
+    return fail(c, RML_E_INVALID, "rml_net_set_resize_tables: bad arguments");
+  DeviceGuard g(c->device);
+  int rc;
+  if ((rc = upload(c, &n.kh[branch], kh, static_cast<size_t>(n.R) * ksh))) return rc;
+  if ((rc = upload(c, &n.kv[branch], kv, static_cast<size_t>(n.R) * ksv))) return rc;
+  if ((rc = upload(c, reinterpret_cast<int32_t**>(&n.bh[branch]), bh, static_cast<size_t>(n.R) * 2))) return rc;
+  if ((rc = upload(c, reinterpret_cast<int32_t**>(&n.bv[branch]), bv, static_cast<size_t>(n.R) * 2))) return rc;
+  n.ksh[branch] = ksh; n.ksv[branch] = ksv;
+  return RML_OK;
+}
+
+int rml_net_add_conv(rml_ctx* c, int layer, int branch, int cin, int cout, int act,
+                     const float* w_hwio, const float* bias) {
+  if (!c) return RML_E_INVALID;
+  Net& n = c->net;
+  if (layer < 0 || layer > 8 || branch < 0 || branch > 2 || cin <= 0 || cout <= 0 ||
+      cout % kConvCoutTile || act < 0 || act > 2 || !w_hwio || !bias)
+    return fail(c, RML_E_INVALID, "rml_net_add_conv: bad arguments (cout must be a multiple of 32)");
+  if (9 * cin * kConvCoutTile * 4 > 200 * 1024)
+    return fail(c, RML_E_UNSUPPORTED, "rml_net_add_conv: cin=%d too large for the smem-resident weights", cin);
+  if (static_cast<int>(n.convs.size()) <= layer) n.convs.resize(layer + 1);
+  NetConv& cv = n.convs[layer];
+  if (cv.cin && (cv.cin != cin || cv.cout != cout || cv.act != act))
+    return fail(c, RML_E_INVALID, "rml_net_add_conv: branches of layer %d disagree", layer);
+  cv.cin = cin; cv.cout = cout; cv.act = act;
+  DeviceGuard g(c->device);
+  int rc;
+  if ((rc = upload(c, &cv.w[branch], w_hwio, static_cast<size_t>(9) * cin * cout))) return rc;
+  if ((rc = upload(c, &cv.bias[branch], bias, static_cast<size_t>(cout)))) return rc;
+  return RML_OK;
+}
+
+int rml_net_set_dense(rml_ctx* c, int K, const uint16_t* w1t_bf16, const float* b1, int act1,
+                      const float* w2, const float* b2, int act2, const float* w3, const float* b3) {
+  if (!c) return RML_E_INVALID;
+  Net& n = c->net;
+  if (K <= 0 || K % kK5BlockK || !w1t_bf16 || !b1 || !w2 || !b2 || !w3 || !b3)
+    return fail(c, RML_E_INVALID, "rml_net_set_dense: bad arguments (K must be a multiple of 64)");
+  DeviceGuard g(c->device);
+  int rc;
+  if ((rc = upload(c, &n.w1t, w1t_bf16, static_cast<size_t>(64) * K))) return rc;
+  if ((rc = upload(c, &n.b1, b1, 64))) return rc;
+  if ((rc = upload(c, &n.w2, w2, 64 * 64))) return rc;
+  if ((rc = upload(c, &n.b2, b2, 64))) return rc;
+  if ((rc = upload(c, &n.w3, w3, static_cast<size_t>(64) * n.C))) return rc;
+  if ((rc = upload(c, &n.b3, b3, n.C))) return rc;
+  n.K = K; n.act1 = act1; n.act2 = act2;
+  return RML_OK;
+}
+
+static int encode_bf16_map(rml_ctx* c, CUtensorMap* map, const void* base, int64_t rows, int K, int box_rows) {
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(K) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kK5BlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = c->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, RML_E_CUDA, "cuTensorMapEncodeTiled(bf16) failed: %d", (int)r);
+  return RML_OK;
+}
+
+// spatial size after the conv tower and consistency of the declared shapes
+static int net_out_hw(const Net& n) {
+  int hw = n.R;
+  for (size_t l = 0; l < n.convs.size(); ++l) hw = (hw + 1) / 2;
+  return hw;
+}
+
+int rml_net_finish(rml_ctx* c) {
+  if (!c) return RML_E_INVALID;
+  Net& n = c->net;
+  if (n.convs.empty() || !n.w1t) return fail(c, RML_E_INVALID, "rml_net_finish: layers missing");
+  int cin = 1;
+  for (size_t l = 0; l < n.convs.size(); ++l) {
+    const NetConv& cv = n.convs[l];
+    for (int b = 0; b < 3; ++b)
+      if (!cv.w[b]) return fail(c, RML_E_INVALID, "conv layer %zu branch %d missing", l, b);
+    if (cv.cin != cin) return fail(c, RML_E_INVALID, "conv layer %zu: cin=%d, expected %d", l, cv.cin, cin);
+    cin = cv.cout;
+  }
+  for (int b = 0; b < 3; ++b)
+    if (!n.kh[b]) return fail(c, RML_E_INVALID, "resize tables of branch %d missing", b);
+  const int hw = net_out_hw(n);
+  if (3 * hw * hw * cin != n.K)
+    return fail(c, RML_E_INVALID, "dense K=%d but the conv towers produce 3*%d*%d*%d", n.K, hw, hw, cin);
+  DeviceGuard g(c->device);
+  int rc = encode_bf16_map(c, &n.map_w1, n.w1t, 64, n.K, 64);
+  if (rc) return rc;
+  n.ready = true;
+  return RML_OK;
+}
+
+static size_t net_core_bytes_per_scan(const rml_ctx* c) {
+  const Net& n = c->net;
+  size_t img = static_cast<size_t>(3) * n.R * n.R * 4;
+  size_t act = 0;
+  int hw = n.R;
+  for (size_t l = 0; l + 1 < n.convs.size(); ++l) {
+    hw = (hw + 1) / 2;
+    size_t a = static_cast<size_t>(3) * hw * hw * n.convs[l].cout * 4;
+    if (a > act) act = a;
+  }
+  // images | two ping-pong fp32 activation buffers | bf16 flattened tower output
+  return img + 2 * act + static_cast<size_t>(n.K) * 2;
+}
+static size_t net_bytes_per_scan(const rml_ctx* c) {
+  // ... | f32 features of the chunk (rml_net_predict only)
+  return net_core_bytes_per_scan(c) + static_cast<size_t>(feature_len(c, RML_MASK_ALL)) * 4;
+}
+
+size_t rml_net_workspace_bytes(const rml_ctx* c, int64_t chunk) {
+  if (!c || !c->net.ready || chunk <= 0) return 0;
+  return net_bytes_per_scan(c) * static_cast<size_t>(chunk) + 4096;
+}
+
+static int net_resize(rml_ctx* c, const float* feats, int64_t n_scans, float* images, cudaStream_t st) {
+  Net& n = c->net;
+  ResizeParams rp;
+  rp.feats = feats; rp.images = images; rp.B = n_scans; rp.F = feature_len(c, RML_MASK_ALL); rp.R = n.R;
+  const int ph[3] = {c->sx, c->sy, c->sx}, pw[3] = {c->sz, c->sz, c->sy};
+  const int poff[3] = {0, c->sx * c->sz, c->sx * c->sz + c->sy * c->sz};
+  int smem_max = 0;
+  for (int b = 0; b < 3; ++b) {
+    rp.ph[b] = ph[b]; rp.pw[b] = pw[b]; rp.poff[b] = poff[b];
+    rp.kh[b] = n.kh[b]; rp.kv[b] = n.kv[b]; rp.bh[b] = n.bh[b]; rp.bv[b] = n.bv[b];
+    rp.ksh[b] = n.ksh[b]; rp.ksv[b] = n.ksv[b];
+    const int sm = (ph[b] * pw[b] + ph[b] * n.R) * 4;
+    if (sm > smem_max) smem_max = sm;
+  }
+  RML_CUDA(c, cudaFuncSetAttribute(k3_resize_pil, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  const int gx = static_cast<int>(n_scans < 4ll * c->num_sms ? n_scans : 4ll * c->num_sms);
+  k3_resize_pil<<<dim3(gx, 3), 256, smem_max, st>>>(rp);
+  RML_CUDA(c, cudaGetLastError());
+  ++c->launches;
+  return RML_OK;
+}
+
+// feats != null: K3 resize into the workspace first; else images_in [n][3][R][R] is used as is
+static int net_forward_chunk(rml_ctx* c, const float* feats, const float* images_in, int64_t n_scans,
+                             char* ws, float* proba, float* logits, int32_t* label, cudaStream_t st,
+                             uint16_t* flat_out = nullptr) {
+  Net& n = c->net;
+  size_t img_b = align256(static_cast<size_t>(n_scans) * 3 * n.R * n.R * 4);
+  size_t act = 0;
+  {
+    int hw = n.R;
+    for (size_t l = 0; l + 1 < n.convs.size(); ++l) {
+      hw = (hw + 1) / 2;
+      size_t a = static_cast<size_t>(3) * hw * hw * n.convs[l].cout * 4;
+      if (a > act) act = a;
+    }
+  }
+  size_t act_b = align256(act * static_cast<size_t>(n_scans));
+  float* images = reinterpret_cast<float*>(ws);
+  float* ping = reinterpret_cast<float*>(ws + img_b);
+  float* pong = reinterpret_cast<float*>(ws + img_b + act_b);
+  uint16_t* flat = reinterpret_cast<uint16_t*>(ws + img_b + 2 * act_b);
+  if (feats) {
+    int rc = net_resize(c, feats, n_scans, images, st);
+    if (rc) return rc;
+  }
+  // K4 conv towers
+  const float* cur = feats ? images : images_in;
+  int hw = n.R;
+  for (size_t l = 0; l < n.convs.size(); ++l) {
+    const NetConv& cv = n.convs[l];
+    const bool last = l + 1 == n.convs.size();
+    ConvParams cp;
+    cp.in = cur;
+    cp.out = last ? static_cast<void*>(flat) : static_cast<void*>((l & 1) ? pong : ping);
+    for (int b = 0; b < 3; ++b) { cp.w[b] = cv.w[b]; cp.bias[b] = cv.bias[b]; }
+    cp.n_img = n_scans * 3; cp.H = hw; cp.W = hw; cp.Cin = cv.cin; cp.Cout = cv.cout;
+    cp.Ho = (hw + 1) / 2; cp.Wo = (hw + 1) / 2;
+    const int pad_total = (cp.Ho - 1) * 2 + 3 - hw;
+    cp.pad_t = cp.pad_l = pad_total > 0 ? pad_total / 2 : 0;   // TF 'same': extra padding goes after
+    cp.act = cv.act; cp.alpha = n.alpha; cp.out_bf16 = last ? 1 : 0;
+    const int smem = 9 * cv.cin * kConvCoutTile * 4;
+    RML_CUDA(c, cudaFuncSetAttribute(k4_conv3x3s2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t pixels = n_scans * cp.Ho * cp.Wo;
+    int64_t gx = (pixels + 255) / 256;
+    if (gx > 8ll * c->num_sms) gx = 8ll * c->num_sms;
+    k4_conv3x3s2<<<dim3(static_cast<unsigned>(gx), cv.cout / kConvCoutTile, 3), 256, smem, st>>>(cp);
+    RML_CUDA(c, cudaGetLastError());
+    ++c->launches;
+    cur = static_cast<const float*>(cp.out);
+    hw = cp.Ho;
+  }
+  if (flat_out)
+    RML_CUDA(c, cudaMemcpyAsync(flat_out, flat, static_cast<size_t>(n_scans) * n.K * 2, cudaMemcpyDeviceToDevice, st));
+  // K5 dense stack on tcgen05
+  CUtensorMap map_act;
+  int rc = encode_bf16_map(c, &map_act, flat, n_scans, n.K, kK5BlockM);
+  if (rc) return rc;
+  K5Params kp;
+  kp.B = n_scans; kp.k_blocks = n.K / kK5BlockK; kp.C = n.C; kp.head = n.head;
+  kp.act1 = n.act1; kp.act2 = n.act2; kp.alpha = n.alpha;
+  kp.b1 = n.b1; kp.w2 = n.w2; kp.b2 = n.b2; kp.w3 = n.w3; kp.b3 = n.b3;
+  kp.proba = proba; kp.logits = logits; kp.label = label;
+  const int smem5 = k5_smem_bytes();
+  RML_CUDA(c, cudaFuncSetAttribute(k5_dense_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5));
+  const int64_t tiles = (n_scans + kK5BlockM - 1) / kK5BlockM;
+  const int grid = static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
+  k5_dense_stack<<<grid, kK5Threads, smem5, st>>>(map_act, n.map_w1, kp);
+  RML_CUDA(c, cudaGetLastError());
+  ++c->launches;
+  return RML_OK;
+}
+
+int rml_net_forward(rml_ctx* c, const float* feats, int64_t B, void* workspace, size_t workspace_bytes,
+                    float* proba, float* logits, int32_t* label, rml_stream stream) {
+  if (!c) return RML_E_INVALID;
+  if (!c->net.ready) return fail(c, RML_E_NOMODEL, "rml_net_forward: no network loaded");
+  if (!feats || !workspace || !proba || !label || B < 0) return fail(c, RML_E_INVALID, "rml_net_forward: null buffer or B<0");
+  if (B == 0) return RML_OK;
+  DeviceGuard g(c->device);
+  const size_t per = net_bytes_per_scan(c);
+  int64_t chunk = workspace_bytes > 4096 ? static_cast<int64_t>((workspace_bytes - 4096) / per) : 0;
+  if (chunk < 1) return fail(c, RML_E_INVALID, "rml_net_forward: workspace too small (%zu B per scan needed)", per);
+  const int F = feature_len(c, RML_MASK_ALL);
+  const int C = c->net.C;
+  for (int64_t lo = 0; lo < B; lo += chunk) {
+    const int64_t n = (B - lo) < chunk ? (B - lo) : chunk;
+    int rc = net_forward_chunk(c, feats + lo * F, nullptr, n, static_cast<char*>(workspace), proba + lo * C,
+                               logits ? logits + lo * C : nullptr, label + lo, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+  }
+  return RML_OK;
+}
+
+// dnn.py:240-254 alone: scaled projections -> [B][3][R][R] float32 (the Keras model's inputs)
+int rml_net_resize(rml_ctx* c, const float* feats, int64_t B, float* images, rml_stream stream) {
+  if (!c) return RML_E_INVALID;
+  if (!c->net.kh[0] || !c->net.kh[1] || !c->net.kh[2]) return fail(c, RML_E_NOMODEL, "rml_net_resize: resize tables not loaded");
+  if (!feats || !images || B < 0) return fail(c, RML_E_INVALID, "rml_net_resize: null buffer or B<0");
+  if (B == 0) return RML_OK;
+  DeviceGuard g(c->device);
+  return net_resize(c, feats, B, images, static_cast<cudaStream_t>(stream));
+}
+
+// Keras model.predict([XZ, YZ, XY]) on already preprocessed inputs: images [B][3][R][R]
+int rml_net_forward_images(rml_ctx* c, const float* images, int64_t B, void* workspace,
+                           size_t workspace_bytes, float* proba, float* logits, int32_t* label,
+                           uint16_t* tower_bf16, rml_stream stream) {
+  if (!c) return RML_E_INVALID;
+  if (!c->net.ready) return fail(c, RML_E_NOMODEL, "rml_net_forward_images: no network loaded");
+  if (!images || !workspace || !proba || !label || B < 0) return fail(c, RML_E_INVALID, "rml_net_forward_images: null buffer or B<0");
+  if (B == 0) return RML_OK;
+  DeviceGuard g(c->device);
+  const size_t per = net_bytes_per_scan(c);
+  int64_t chunk = workspace_bytes > 4096 ? static_cast<int64_t>((workspace_bytes - 4096) / per) : 0;
+  if (chunk < 1) return fail(c, RML_E_INVALID, "rml_net_forward_images: workspace too small (%zu B per scan needed)", per);
+  const int C = c->net.C;
+  const size_t img_elems = static_cast<size_t>(3) * c->net.R * c->net.R;
+  for (int64_t lo = 0; lo < B; lo += chunk) {
+    const int64_t n = (B - lo) < chunk ? (B - lo) : chunk;
+    int rc = net_forward_chunk(c, nullptr, images + lo * img_elems, n, static_cast<char*>(workspace),
+                               proba + lo * C, logits ? logits + lo * C : nullptr, label + lo,
+                               static_cast<cudaStream_t>(stream),
+                               tower_bf16 ? tower_bf16 + lo * static_cast<int64_t>(c->net.K) : nullptr);
+    if (rc) return rc;
+  }
+  return RML_OK;
+}
+
+
+// cubes -> K1 (projection + (p-127.5)/127.5, dnn.py:202-205) -> K3 -> K4 -> K5, chunked
+int rml_net_predict(rml_ctx* c, const float* cubes, int64_t B, int mode, const int32_t* ijk,
+                    void* workspace, size_t workspace_bytes, float* proba, int32_t* label,
+                    rml_stream stream) {
+  if (!c) return RML_E_INVALID;
+  if (!c->net.ready) return fail(c, RML_E_NOMODEL, "rml_net_predict: no network loaded");
+  if (!cubes || !workspace || !proba || !label || B < 0) return fail(c, RML_E_INVALID, "rml_net_predict: null buffer or B<0");
+  if (B == 0) return RML_OK;
+  DeviceGuard g(c->device);
+  const size_t per = net_bytes_per_scan(c);
+  int64_t chunk = workspace_bytes > 4096 ? static_cast<int64_t>((workspace_bytes - 4096) / per) : 0;
+  if (chunk < 1) return fail(c, RML_E_INVALID, "rml_net_predict: workspace too small (%zu B per scan needed)", per);
+  const int F = feature_len(c, RML_MASK_ALL);
+  const int C = c->net.C;
+  const size_t cube_elems = static_cast<size_t>(c->sx) * c->sy * c->sz;
+  const int saved = c->aff_enabled;
+  const float so = c->aff_offset, ss = c->aff_scale;
+  c->aff_enabled = 1; c->aff_offset = 127.5f; c->aff_scale = 127.5f;
+  int rc = RML_OK;
+  for (int64_t lo = 0; lo < B && rc == RML_OK; lo += chunk) {
+    const int64_t n = (B - lo) < chunk ? (B - lo) : chunk;
+    char* ws = static_cast<char*>(workspace);
+    // features of the chunk live behind the network buffers (fixed offset for every chunk)
+    float* feats = reinterpret_cast<float*>(ws + align256(net_core_bytes_per_scan(c) * static_cast<size_t>(chunk) + 1024));
+    rc = project_impl(c, cubes + lo * cube_elems, n, mode, ijk ? ijk + lo * 3 : nullptr, RML_MASK_ALL,
+                      RML_F32, feats, nullptr, static_cast<cudaStream_t>(stream));
+    if (rc == RML_OK)
+      rc = net_forward_chunk(c, feats, nullptr, n, ws, proba + lo * C, nullptr, label + lo, static_cast<cudaStream_t>(stream));
+  }
+  c->aff_enabled = saved; c->aff_offset = so; c->aff_scale = ss;
+  return rc;
+}
 
 }  // extern "C"
