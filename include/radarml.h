@@ -103,6 +103,28 @@ int rml_process_samples(rml_ctx* ctx, const float* xz_dev, const float* yz_dev,
 int rml_matrix_indices(rml_ctx* ctx, const double* xyz_dev, int64_t B, int32_t* ijk_dev,
                        rml_stream stream);
 
+/* common.py:45-80 DerivedTarget.get_derived_targets: per scan, the num_targets indices with the
+ * largest axis sums of the raw cube along theta (i), phi (j) and r (k), ascending by sum like
+ * np.argsort (the last triple is the strongest).  ijk_dev int32 [B][num_targets][3];
+ * sums_dev (nullable) float32 [B][sx+sy+sz] = theta | phi | r sums. */
+int rml_derive_targets(rml_ctx* ctx, const float* cubes_dev, int64_t B, int num_targets,
+                       int32_t* ijk_dev, float* sums_dev, rml_stream stream);
+/* common.py:143-144 scipy.ndimage.zoom(p, proj_zoom[i]) (order-3 spline) for arenas that differ
+ * from the training arena (predict.py:34-54, README.md:207).  For fixed sizes the zoom is a
+ * separable linear operator: a_rows [out_h][in_h], a_cols [out_w][in_w] (HOST float64,
+ * extracted from scipy by the caller).  proj: 0 xz, 1 yz, 2 xy. */
+int rml_set_zoom(rml_ctx* ctx, int proj, int in_h, int in_w, int out_h, int out_w,
+                 const double* a_rows_host, const double* a_cols_host);
+int rml_zoom_feature_len(const rml_ctx* ctx, uint32_t mask);
+/* common.process_samples with zoom: projection p of scan b starts at p_dev + b*stride_p
+ * (elements), so both separate [B][h][w] arrays and rml_project feature rows can be fed.
+ * feats_dev float32 [B][rml_zoom_feature_len(mask)], scaled by the rml_set_affine transform
+ * when scale != 0. */
+int rml_process_samples_zoom(rml_ctx* ctx, const float* xz_dev, int64_t stride_xz,
+                             const float* yz_dev, int64_t stride_yz, const float* xy_dev,
+                             int64_t stride_xy, int64_t B, uint32_t mask, int scale,
+                             float* feats_dev, rml_stream stream);
+
 /* ---- K2: predict.py:56-70 classifier() -> model.predict_proba chain -------------------- */
 /* feats_dev as written by rml_project (dtype RML_U8 needs norms_dev) or float32 (n,F)
  * features already scaled like common.process_samples(scale=True).

@@ -74,6 +74,11 @@ SIGNATURES = {
     "rml_project": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _u32, C.c_int, _vp, _vp, _vp]),
     "rml_process_samples": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _u32, C.c_int, _vp, _vp]),
     "rml_matrix_indices": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "rml_derive_targets": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp]),
+    "rml_set_zoom": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "rml_zoom_feature_len": (C.c_int, [_vp, _u32]),
+    "rml_process_samples_zoom": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _u32, C.c_int,
+                                           _vp, _vp]),
     "rml_quantize_features": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp]),
     "rml_score": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, _f64, _vp, _vp, _vp, _vp, _vp]),
     "rml_predict_workspace_bytes": (_sz, [_vp, _i64]),

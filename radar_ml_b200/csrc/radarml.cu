@@ -16,6 +16,7 @@
 #include "k1_project.cuh"
 #include "k2_score.cuh"
 #include "k3_net.cuh"
+#include "k0_extras.cuh"
 
 using namespace rml;
 
@@ -91,6 +92,10 @@ struct rml_ctx {
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   HostPipe pipe;
   Net net;
+  // zoom operators (common.py:143 ndimage.zoom as separable matrices), per projection
+  double* zoom_ar[3] = {nullptr, nullptr, nullptr};
+  double* zoom_ac[3] = {nullptr, nullptr, nullptr};
+  int zoom_ih[3] = {0, 0, 0}, zoom_iw[3] = {0, 0, 0}, zoom_oh[3] = {0, 0, 0}, zoom_ow[3] = {0, 0, 0};
 };
 
 namespace {
@@ -398,6 +403,7 @@ int rml_destroy(rml_ctx* c) {
   free_model(c->model);
   free_pipe(c->pipe);
   free_net(c->net);
+  for (int q = 0; q < 3; ++q) { cudaFree(c->zoom_ar[q]); cudaFree(c->zoom_ac[q]); }
   cudaFree(c->status);
   delete c;
   return RML_OK;
@@ -666,6 +672,91 @@ int rml_check_status(rml_ctx* c, rml_stream stream) {
 
 int64_t rml_launch_count(const rml_ctx* c) { return c ? c->launches : 0; }
 
+
+// ------------------------------------------------------------------------------ §8f callers
+int rml_derive_targets(rml_ctx* c, const float* cubes, int64_t B, int num_targets, int32_t* ijk,
+                       float* sums, rml_stream stream) {
+  if (!c) return RML_E_INVALID;
+  if (!cubes || !ijk || B < 0 || num_targets < 1 || num_targets > kMaxTargets ||
+      num_targets > c->sx || num_targets > c->sy || num_targets > c->sz)
+    return fail(c, RML_E_INVALID, "rml_derive_targets: bad arguments");
+  if (B == 0) return RML_OK;
+  DeviceGuard g(c->device);
+  DeriveParams p;
+  p.cubes = cubes; p.ijk = ijk; p.sums = sums; p.B = B; p.sx = c->sx; p.sy = c->sy; p.sz = c->sz;
+  p.T = num_targets;
+  const int smem = (c->sx + c->sy + c->sz + 8 * c->sz + c->sx * c->sy) * 4;
+  RML_CUDA(c, cudaFuncSetAttribute(k0_derive_targets, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = static_cast<int>(B < 8ll * c->num_sms ? B : 8ll * c->num_sms);
+  k0_derive_targets<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  RML_CUDA(c, cudaGetLastError());
+  ++c->launches;
+  return RML_OK;
+}
+
+int rml_set_zoom(rml_ctx* c, int proj, int in_h, int in_w, int out_h, int out_w,
+                 const double* a_rows, const double* a_cols) {
+  if (!c) return RML_E_INVALID;
+  if (proj < 0 || proj > 2 || in_h <= 0 || in_w <= 0 || out_h <= 0 || out_w <= 0 || !a_rows || !a_cols)
+    return fail(c, RML_E_INVALID, "rml_set_zoom: bad arguments");
+  if (static_cast<size_t>(in_h) * out_w * 8 + static_cast<size_t>(in_h) * in_w * 4 > 200 * 1024)
+    return fail(c, RML_E_UNSUPPORTED, "rml_set_zoom: projection too large for the smem-resident zoom");
+  DeviceGuard g(c->device);
+  cudaDeviceSynchronize();
+  cudaFree(c->zoom_ar[proj]); cudaFree(c->zoom_ac[proj]);
+  c->zoom_ar[proj] = c->zoom_ac[proj] = nullptr;
+  int rc;
+  if ((rc = upload(c, &c->zoom_ar[proj], a_rows, static_cast<size_t>(out_h) * in_h))) return rc;
+  if ((rc = upload(c, &c->zoom_ac[proj], a_cols, static_cast<size_t>(out_w) * in_w))) return rc;
+  c->zoom_ih[proj] = in_h; c->zoom_iw[proj] = in_w; c->zoom_oh[proj] = out_h; c->zoom_ow[proj] = out_w;
+  return RML_OK;
+}
+
+int rml_zoom_feature_len(const rml_ctx* c, uint32_t mask) {
+  if (!c) return RML_E_INVALID;
+  int f = 0;
+  for (int q = 0; q < 3; ++q)
+    if (mask & (1u << q)) f += c->zoom_oh[q] * c->zoom_ow[q];
+  return f;
+}
+
+int rml_process_samples_zoom(rml_ctx* c, const float* xz, int64_t stride_xz, const float* yz,
+                             int64_t stride_yz, const float* xy, int64_t stride_xy, int64_t B,
+                             uint32_t mask, int scale, float* feats, rml_stream stream) {
+  if (!c) return RML_E_INVALID;
+  if (!feats || B < 0 || (mask & RML_MASK_ALL) == 0)
+    return fail(c, RML_E_INVALID, "rml_process_samples_zoom: bad arguments");
+  const float* src[3] = {xz, yz, xy};
+  const int64_t strides[3] = {stride_xz, stride_yz, stride_xy};
+  for (int q = 0; q < 3; ++q)
+    if ((mask & (1u << q)) && (!src[q] || !c->zoom_ar[q]))
+      return fail(c, RML_E_INVALID, "rml_process_samples_zoom: projection %d missing or rml_set_zoom not called", q);
+  if (B == 0) return RML_OK;
+  DeviceGuard g(c->device);
+  ZoomParams p;
+  int off = 0, smem = 0;
+  for (int q = 0; q < 3; ++q) {
+    const bool on = mask & (1u << q);
+    p.proj[q] = on ? src[q] : nullptr;
+    p.pstride[q] = strides[q];
+    p.ih[q] = c->zoom_ih[q]; p.iw[q] = c->zoom_iw[q]; p.oh[q] = c->zoom_oh[q]; p.ow[q] = c->zoom_ow[q];
+    p.ar[q] = c->zoom_ar[q]; p.ac[q] = c->zoom_ac[q];
+    p.off[q] = off;
+    if (on) {
+      off += p.oh[q] * p.ow[q];
+      const int sm = p.ih[q] * p.ow[q] * 8 + p.ih[q] * p.iw[q] * 4;
+      if (sm > smem) smem = sm;
+    }
+  }
+  p.feats = feats; p.B = B; p.F = off; p.scale = scale;
+  p.offset = c->aff_offset; p.scale_value = c->aff_scale;
+  RML_CUDA(c, cudaFuncSetAttribute(k0_zoom_concat, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int gx = static_cast<int>(B < 4ll * c->num_sms ? B : 4ll * c->num_sms);
+  k0_zoom_concat<<<dim3(gx, 3), 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  RML_CUDA(c, cudaGetLastError());
+  ++c->launches;
+  return RML_OK;
+}
 
 // ------------------------------------------------------------------------------ networks
 int rml_net_begin(rml_ctx* c, int resize_to, int n_classes, int head, float alpha) {

@@ -161,6 +161,41 @@ class Engine:
                                                      1 if scale else 0, _ptr(out), self._stream()))
         return out
 
+    def derive_targets(self, cubes, num_targets=1, want_sums=False):
+        """common.py:45-80 on device: cubes [B,sx,sy,sz] -> ijk int32 [B,T,3] (ascending by sum;
+        last = strongest) and optionally the float32 axis sums [B, sx+sy+sz]."""
+        self._check_cubes(cubes)
+        B = cubes.shape[0]
+        ijk = torch.empty((B, num_targets, 3), device=self.device, dtype=torch.int32)
+        sums = torch.empty((B, sum(self.dims)), device=self.device, dtype=torch.float32) if want_sums else None
+        if B:
+            check(self.ctx, self.lib.rml_derive_targets(self.ctx, _ptr(cubes), B, num_targets, _ptr(ijk),
+                                                        _ptr(sums), self._stream()))
+        return (ijk, sums) if want_sums else ijk
+
+    def set_zoom(self, proj, a_rows, a_cols):
+        """Separable ndimage.zoom operator of projection ``proj`` (0 xz, 1 yz, 2 xy):
+        a_rows [out_h, in_h], a_cols [out_w, in_w] float64 host arrays."""
+        ar = np.ascontiguousarray(a_rows, dtype=np.float64)
+        ac = np.ascontiguousarray(a_cols, dtype=np.float64)
+        check(self.ctx, self.lib.rml_set_zoom(self.ctx, proj, ar.shape[1], ac.shape[1], ar.shape[0],
+                                              ac.shape[0], _np_ptr(ar), _np_ptr(ac)))
+
+    def process_samples_zoom(self, xz, yz, xy, mask=MASK_ALL, scale=False, strides=None):
+        """common.process_samples with proj_zoom != 1 (operators set by ``set_zoom``)."""
+        m = mask_bits(mask)
+        ref = next(t for t in (xz, yz, xy) if t is not None)
+        B = ref.shape[0]
+        F = self.lib.rml_zoom_feature_len(self.ctx, m)
+        out = torch.empty((B, F), device=self.device, dtype=torch.float32)
+        if strides is None:
+            strides = [0 if t is None else int(t[0].numel()) for t in (xz, yz, xy)]
+        if B:
+            check(self.ctx, self.lib.rml_process_samples_zoom(
+                self.ctx, _ptr(xz), strides[0], _ptr(yz), strides[1], _ptr(xy), strides[2], B, m,
+                1 if scale else 0, _ptr(out), self._stream()))
+        return out
+
     def matrix_indices(self, xyz):
         """xyz [B,3] float64 CUDA -> ijk [B,3] int32 (common.calculate_matrix_indices)."""
         xyz = xyz.to(device=self.device, dtype=torch.float64).contiguous()

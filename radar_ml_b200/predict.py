@@ -92,6 +92,45 @@ def classify_cubes(cubes, model, le=None, min_proba=0.7, mode='max', ijk=None,
     return lab, best, known, P, names
 
 
+def _classify_zoomed(cubes, ijk, gm, le, min_proba, proj_mask, proj_zoom, dims):
+    """predict.py:102-119 when the scan arena differs from the training arena: slices at the
+    scan arena's size (K1), ndimage.zoom to the training size as separable operators
+    (common.py:143), /255, then the general-precision scorer (zoomed values are not integers)."""
+    import torch
+    eng = gm.engine
+    size_x, size_y, size_z = dims
+    saved = eng.dims
+    eng.set_arena(size_x, size_y, size_z)
+    try:
+        eng.set_affine(0.0, common.RADAR_MAX, False)
+        d = torch.from_numpy(np.ascontiguousarray(cubes, dtype=np.float32)).to(eng.device)
+        raw = eng.project(d, mode='slice', ijk=torch.from_numpy(np.ascontiguousarray(ijk, dtype=np.int32)),
+                          mask=common.ProjMask(True, True, True))
+        eng.check_status()
+        shapes = [(size_x, size_z), (size_y, size_z), (size_x, size_y)]
+        offs = [0, size_x * size_z, size_x * size_z + size_y * size_z]
+        views = []
+        for q in range(3):
+            if proj_mask[q]:
+                h, w = shapes[q]
+                eng.set_zoom(q, common.zoom_operator(h, proj_zoom[q][0]), common.zoom_operator(w, proj_zoom[q][1]))
+                views.append(raw[:, offs[q]:])
+            else:
+                views.append(None)
+        eng.set_affine(0.0, common.RADAR_MAX, True)
+        F = raw.shape[1]
+        feats = eng.process_samples_zoom(views[0], views[1], views[2], mask=proj_mask, scale=True,
+                                         strides=[F, F, F])
+    finally:
+        eng.set_affine(0.0, common.RADAR_MAX, True)
+        eng.set_arena(*saved)
+    proba, label, known = eng.score(feats, None, min_proba)
+    P, lab, known = proba.cpu().numpy(), label.cpu().numpy(), known.cpu().numpy().astype(bool)
+    best = P[np.arange(P.shape[0]), lab]
+    names = np.where(known, np.asarray(le.classes_)[lab], 'Unknown')
+    return lab, best, known, P, names
+
+
 def predict(min_proba, model, le, proj_mask, radar=None, max_scans=None):
     """predict.py:72-131 — the live loop: trigger, locate targets, slice, classify.
 
@@ -119,17 +158,19 @@ def predict(min_proba, model, le, proj_mask, radar=None, max_scans=None):
             raw_image_np = np.array(raw_image, dtype=np.float32)
             proj_zoom = calc_proj_zoom(train_size_x, train_size_y, train_size_z,
                                        size_x, size_y, size_z)
-            if not common._unit_zoom(proj_zoom, proj_mask):
-                raise NotImplementedError('scan arena differs from the training arena; zoom is '
-                                          'not supported by the CUDA path yet (SURVEY §8f F2)')
             n = len(targets)
             xs = np.array([t.xPosCm for t in targets], dtype=np.float64)
             ys = np.array([t.yPosCm for t in targets], dtype=np.float64)
             zs = np.array([t.zPosCm for t in targets], dtype=np.float64)
             ijk = np.asarray(common.calculate_matrix_indices(xs, ys, zs, size_x, size_y, size_z))
             cubes = np.ascontiguousarray(np.broadcast_to(raw_image_np, (n,) + raw_image_np.shape))
-            lab, best, known, P, names = classify_cubes(cubes, gm, le, min_proba, mode='slice',
-                                                        ijk=ijk.reshape(n, 3), proj_mask=proj_mask)
+            if common._unit_zoom(proj_zoom, proj_mask):
+                lab, best, known, P, names = classify_cubes(cubes, gm, le, min_proba, mode='slice',
+                                                            ijk=ijk.reshape(n, 3), proj_mask=proj_mask)
+            else:
+                lab, best, known, P, names = _classify_zoomed(
+                    cubes, ijk.reshape(n, 3), gm, le, min_proba, proj_mask, proj_zoom,
+                    (size_x, size_y, size_z))
             for t, target in enumerate(targets):
                 logger.info('**********')
                 logger.info('Target #{}:\nx: {}\ny: {}\nz: {}\namplitude: {}\n'.format(

@@ -306,8 +306,6 @@ def test_drop_in_common_and_predict_api(eng, small_problem):
         name, proba = predict.classifier(obs, cal, le, 0.7)       # sklearn object accepted as-is
         name_o, proba_o = restate.classifier(obs, p, le.classes_, 0.7)
         assert name == name_o and abs(proba - proba_o) < PROBA_TOL
-    with pytest.raises(NotImplementedError):
-        common.process_samples([(xz, yz, xy)], proj_zoom=predict.calc_proj_zoom(22, 31, 176, 11, 31, 176))
     assert common.calculate_matrix_indices(12.5, -3.0, 140.0, 22, 31, 176) == \
         restate.calculate_matrix_indices(12.5, -3.0, 140.0, 22, 31, 176)
 
@@ -377,3 +375,114 @@ def test_error_paths(eng, small_problem):
         eng.check_status()                                   # numpy would raise IndexError
     empty = torch.zeros((0, 22, 31, 176), device="cuda")
     assert eng.project(empty).shape == (0, 10010)            # empty batch is a no-op
+
+
+# --------------------------------------------------------------------------- §8f callers
+def test_derived_targets_match_reference_formula(eng, small_problem):
+    """common.py:45-80: axis sums + top-k (exact for integer-valued sensor data)."""
+    import torch
+    from radar_ml_b200 import common
+    common.set_engine(eng)
+    cubes = small_problem["cubes"][:40]
+    ijk, sums = eng.derive_targets(torch.from_numpy(cubes).cuda(), num_targets=3, want_sums=True)
+    ijk, sums = ijk.cpu().numpy(), sums.cpu().numpy()
+    for s in range(40):
+        d = cubes[s]
+        sx = np.sum(np.sum(d, axis=1), axis=1)      # find_max_indices(1, 1)
+        sy = np.sum(np.sum(d, axis=0), axis=1)      # find_max_indices(0, 1)
+        sz = np.sum(np.sum(d, axis=0), axis=0)      # find_max_indices(0, 0)
+        assert np.array_equal(sums[s], np.concatenate([sx, sy, sz]))
+        for a, sm in enumerate((sx, sy, sz)):
+            top = np.argpartition(sm, -3)[-3:]
+            want = top[np.argsort(sm[top])]
+            if len(set(sm[want].tolist())) == 3 and sm[want[0]] > np.sort(sm)[-4]:   # no ties
+                assert np.array_equal(ijk[s, :, a], want)
+    # reference-shaped API: one cube -> [DerivedTarget]
+    t = common.DerivedTarget.get_derived_targets(cubes[0].tolist(), 22, 31, 176, num_targets=1)
+    assert len(t) == 1 and (t[0].i, t[0].j, t[0].k) == tuple(int(v) for v in ijk[0, -1])
+    th = common.THETA_MIN + t[0].i * (common.THETA_MAX - common.THETA_MIN) / 21
+    ph = common.PHI_MIN + t[0].j * (common.PHI_MAX - common.PHI_MIN) / 30
+    r = common.R_MIN + t[0].k * (common.R_MAX - common.R_MIN) / 175
+    assert np.allclose((t[0].xPosCm, t[0].yPosCm, t[0].zPosCm), common.spherical_to_cartesian(r, th, ph))
+    assert t[0].amplitude is None
+
+
+def test_zoomed_process_samples_matches_scipy(eng):
+    """common.py:143 ndimage.zoom for a scan arena that differs from the training arena."""
+    from scipy import ndimage
+    from radar_ml_b200 import common, predict
+    common.set_engine(eng)
+    rng = np.random.default_rng(12)
+    sx, sy, sz = 11, 31, 150                       # smaller arena than the 22x31x176 training one
+    samples = [(rng.integers(0, 256, (sx, sz)).astype(np.float32),
+                rng.integers(0, 256, (sy, sz)).astype(np.float32),
+                rng.integers(0, 256, (sx, sy)).astype(np.float32)) for _ in range(5)]
+    zoom = predict.calc_proj_zoom(22, 31, 176, sx, sy, sz)
+    for mask in ((True, True, True), (False, True, True)):
+        got = common.process_samples(samples, proj_mask=common.ProjMask(*mask), proj_zoom=zoom, scale=True)
+        want = np.array([np.concatenate([ndimage.zoom(p, zoom[i]) for i, p in enumerate(t) if mask[i]],
+                                        axis=None) / 255. for t in samples])
+        assert got.shape == want.shape and got.dtype == np.float32
+        assert got.shape[1] == sum(n for n, m in zip((22 * 176, 31 * 176, 22 * 31), mask) if m)
+        assert np.abs(got - want).max() < 1e-6
+
+
+def test_predict_loop_with_arena_mismatch(eng, small_problem):
+    """predict.predict when GetRawImage returns a smaller arena (zoom path, README.md:207)."""
+    from scipy import ndimage
+    from oracle import restate, synth
+    from radar_ml_b200 import common, predict
+    common.set_engine(eng)
+    rng = np.random.default_rng(3)
+    raw = rng.integers(0, 256, (11, 31, 88)).astype(np.float32)
+
+    class Target:
+        xPosCm, yPosCm, zPosCm, amplitude = 8.0, -6.0, 150.0, 1.0
+
+    class FakeRadar:
+        def Trigger(self): pass
+        def GetSensorTargets(self): return [Target()]
+        def GetRawImage(self): return raw.tolist(), 11, 31, 88, 0.0
+        def Stop(self): pass
+        def Disconnect(self): pass
+        def Clean(self): pass
+
+    le = synth.LabelEncoderLike()
+    res = predict.predict(0.7, small_problem["cal"], le, common.ProjMask(True, True, True),
+                          radar=FakeRadar(), max_scans=1)
+    i, j, k = restate.calculate_matrix_indices(8.0, -6.0, 150.0, 11, 31, 88)
+    zoom = restate.calc_proj_zoom(22, 31, 176, 11, 31, 88)
+    t = (raw[:, j, :], raw[i, :, :], raw[:, :, k])
+    obs = restate.process_samples([t], proj_zoom=zoom, scale=True)       # scipy, like the reference
+    name, proba = restate.classifier(obs, small_problem["params"], le.classes_, 0.7)
+    assert len(res) == 1 and res[0][0] == name and abs(res[0][1] - proba) < PROBA_TOL
+
+
+def test_dataset_roundtrip_and_evaluate_model(eng, small_problem, tmp_path):
+    """datasets/README.md format + train.py:215-228 evaluate_model on GPU-scored labels."""
+    from sklearn import metrics
+    from oracle import synth
+    from radar_ml_b200 import common, dataset
+    common.set_engine(eng)
+    cubes, y, ijk = (small_problem[k] for k in ("cubes", "y", "ijk"))
+    sl = small_problem["test"]
+    xz, yz, xy = synth.project_max(cubes[sl])
+    names = np.array(synth.CLASSES)[y[sl]]
+    samples = [(xz[i], yz[i], xy[i]) for i in range(len(names))]
+    path = tmp_path / "radar_samples.pickle"
+    dataset.save_dataset(path, samples, list(names) + [])
+    data = dataset.load_datasets([str(path)], prj_dir="")
+    smp, enc, class_names = dataset.filter_and_encode(data, ["cat", "dog", "person"])
+    assert class_names == ["cat", "dog", "person"] and np.array_equal(enc, y[sl])
+    X = dataset.features(smp)
+    assert np.array_equal(X, small_problem["X"][sl])
+    cal = small_problem["cal"]
+    acc, cm, report = dataset.evaluate_model(cal, X, enc, class_names)
+    y_pred = cal.predict(X)
+    assert acc == metrics.accuracy_score(enc, y_pred)
+    assert np.array_equal(cm, metrics.confusion_matrix(enc, y_pred, labels=[0, 1, 2]))
+    ref = metrics.classification_report(enc, y_pred, target_names=class_names, output_dict=True, zero_division=0)
+    for row in report["per_class"]:
+        assert abs(row["precision"] - ref[row["class"]]["precision"]) < 1e-12
+        assert abs(row["recall"] - ref[row["class"]]["recall"]) < 1e-12
+        assert row["support"] == ref[row["class"]]["support"]
