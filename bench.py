@@ -103,17 +103,20 @@ class ClockSampler:
 
     def _run(self):
         nv = self.nv
+        it = 0
         while not self._stop.is_set():
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                for bit, name in self.BITS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                if it % 8 == 0:      # the reasons / power queries are slower than the clock query
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    for bit, name in self.BITS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            time.sleep(0.002)
+            it += 1
+            time.sleep(0.001)
 
     def stop(self):
         self._stop.set()
@@ -350,7 +353,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scans-per-gpu", type=int, default=0)

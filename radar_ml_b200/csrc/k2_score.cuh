@@ -24,7 +24,8 @@
 
 namespace rml {
 
-constexpr int kK2Threads = 192;
+constexpr int kK2EpiWarps = 8;                 // two warps per TMEM lane quarter
+constexpr int kK2Threads = (2 + kK2EpiWarps) * 32;   // 320
 constexpr int kK2BlockM = 128;
 constexpr int kK2BlockKBytes = 128;          // one 128-byte swizzle span of u8 features
 constexpr int kK2MaxTileN = 256;             // columns per accumulator buffer
@@ -39,8 +40,9 @@ struct K2Params {
   int k_blocks;   // padded feature bytes / 128
   int stages;     // smem ring depth (host picks the deepest that fits 227 KB)
   const int32_t* unorm;    // [B]    sum u^2
-  const int32_t* svnorm;   // [n_sv] sum s^2
-  const double* coef;      // [C-1][n_sv]  SVC._dual_coef_
+  const int32_t* svnorm;   // [n_pad] sum s^2 (n_pad = n_tile * n_chunks, zero padded)
+  const double* pairw;     // [C(C-1)/2][n_pad] weight of SV n in OvO pair p (0 outside the pair)
+  int n_pad;
   const double* rho;       // [C(C-1)/2]
   const double* platt_a;   // [C] (or [1] when C == 2)
   const double* platt_b;
@@ -56,12 +58,38 @@ struct K2Params {
 __host__ __device__ constexpr int k2_stage_bytes(int n_tile) {
   return kK2BlockM * kK2BlockKBytes + n_tile * kK2BlockKBytes;
 }
-__host__ __device__ constexpr int k2_smem_bytes(int n_tile, int stages) {
-  return stages * k2_stage_bytes(n_tile) + 1024 /*align slack*/ + 256 /*barriers*/;
+// epilogue tables (svnorm + pair weights) and the half-exchange buffer live in smem too
+__host__ __device__ constexpr int k2_table_bytes(int n_pad, int n_pairs) {
+  return ((n_pad * (4 + 8 * n_pairs) + 127) / 128) * 128 + kK2BlockM * n_pairs * 8;
 }
-inline int k2_pick_stages(int n_tile) {
-  int s = (232448 - 1024 - 256) / k2_stage_bytes(n_tile);
+__host__ __device__ constexpr int k2_smem_bytes(int n_tile, int stages, int n_pad, int n_pairs) {
+  return stages * k2_stage_bytes(n_tile) + 1024 /*align slack*/ + 256 /*barriers*/ +
+         k2_table_bytes(n_pad, n_pairs);
+}
+inline int k2_pick_stages(int n_tile, int n_pad, int n_pairs) {
+  int s = (232448 - 1024 - 256 - k2_table_bytes(n_pad, n_pairs)) / k2_stage_bytes(n_tile);
   return s > kK2MaxStages ? kK2MaxStages : s;
+}
+
+// exp(x) for x <= 0 to ~5e-9 relative: exact range reduction in fp64, the r^3.. tail of the
+// series in fp32, 1 + r + r^2/2 + tail reassembled in fp64 (the epilogue needs ~1e-8; the full
+// fp64 exp() was the latency bottleneck of this kernel).
+__device__ __forceinline__ double exp_neg_fast(double x) {
+  const double fn = rint(x * 1.4426950408889634074);
+  double r = fma(fn, -6.93147180369123816490e-01, x);
+  r = fma(fn, -1.90821492927058770002e-10, r);
+  const float rf = static_cast<float>(r);
+  float q = fmaf(rf, 2.7557319e-6f, 2.4801587e-5f);   // 1/9!, 1/8!
+  q = fmaf(q, rf, 1.9841270e-4f);                      // 1/7!
+  q = fmaf(q, rf, 1.3888889e-3f);                      // 1/6!
+  q = fmaf(q, rf, 8.3333333e-3f);                      // 1/5!
+  q = fmaf(q, rf, 4.1666667e-2f);                      // 1/4!
+  q = fmaf(q, rf, 1.6666667e-1f);                      // 1/3!
+  const float tail = q * rf * rf * rf;
+  const double e = fma(r, fma(r, 0.5, 1.0), 1.0) + static_cast<double>(tail);
+  const int n = static_cast<int>(fn);
+  if (n < -1000) return 0.0;
+  return __hiloint2double(__double2hiint(e) + (n << 20), __double2loint(e));
 }
 
 // scipy.special.expit in float64
@@ -152,6 +180,12 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
   uint64_t* tfull = empty + kK2MaxStages;   // [2]
   uint64_t* tempty = tfull + 2;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  unsigned char* tab = smem + kK2Stages * stage_bytes + 256;
+  int32_t* s_norm = reinterpret_cast<int32_t*>(tab);                                   // [n_pad]
+  double* s_w = reinterpret_cast<double*>(tab + ((p.n_pad * 4 + 7) / 8) * 8);            // [NP][n_pad]
+  double* s_x = reinterpret_cast<double*>(tab + ((p.n_pad * (4 + 8 * NP) + 127) / 128) * 128);  // [128][NP]
+  for (int e = threadIdx.x; e < p.n_pad; e += blockDim.x) s_norm[e] = p.svnorm[e];
+  for (int e = threadIdx.x; e < p.n_pad * NP; e += blockDim.x) s_w[e] = p.pairw[e];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -164,7 +198,7 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], kK2EpiWarps);
     }
     fence_barrier_init();
     tma_prefetch_desc(&map_feats);
@@ -230,82 +264,55 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    // warp w serves TMEM lane quarter (w & 3); the two warps of a quarter take alternate
+    // 16-column groups and the odd half hands its partial pair sums over through smem.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int m = q * 32 + lane;       // row of the tile = scan
     uint32_t ait = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t b = tile * kK2BlockM + m;
       const int un = (b < p.B) ? p.unorm[b] : 0;
-      double acc[C - 1];
       double dec[NP];
 #pragma unroll
-      for (int r = 0; r < C - 1; ++r) acc[r] = 0.0;
-#pragma unroll
       for (int r = 0; r < NP; ++r) dec[r] = 0.0;
-      int cls = 0;
-      int cls_end = p.class_end[0];
       for (int ch = 0; ch < p.n_chunks; ++ch, ++ait) {
         const int ab = ait & 1;
         mbar_wait(&tfull[ab], (ait >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ab * kK2MaxTileN + (static_cast<uint32_t>(q * 32) << 16);
-        for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        for (int c0 = half * 16; c0 < p.n_tile; c0 += 32) {
           uint32_t v[16];
           tmem_ld_32x16(taddr + c0, v);
           tmem_ld_wait();
           const int n0 = ch * p.n_tile + c0;
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const int n = n0 + e;
-            if (n < p.n_sv) {
-              while (n >= cls_end) {
-                // class segment finished: scatter its C-1 partial sums to the OvO pairs
+            const int n = n0 + e;   // padded columns have zero weights (and zero SV rows)
+            const int d2i = un + s_norm[n] - 2 * static_cast<int>(v[e]);
+            const double kv = exp_neg_fast(static_cast<double>(d2i) * p.neg_gamma_s2);
 #pragma unroll
-                for (int cc = 0; cc < C; ++cc) {
-                  if (cls == cc) {
-#pragma unroll
-                    for (int r = 0; r < C - 1; ++r) {
-                      const int o = (r < cc) ? r : r + 1;
-                      const int lo = (cc < o) ? cc : o, hi = (cc < o) ? o : cc;
-                      dec[lo * (2 * C - lo - 1) / 2 + (hi - lo - 1)] += acc[r];
-                      acc[r] = 0.0;
-                    }
-                  }
-                }
-                ++cls;
-                cls_end = p.class_end[cls];
-              }
-              const int d2i = un + __ldg(&p.svnorm[n]) - 2 * static_cast<int>(v[e]);
-              const double kv = exp(static_cast<double>(d2i) * p.neg_gamma_s2);
-#pragma unroll
-              for (int r = 0; r < C - 1; ++r) acc[r] = fma(__ldg(&p.coef[r * p.n_sv + n]), kv, acc[r]);
-            }
+            for (int r = 0; r < NP; ++r) dec[r] = fma(s_w[r * p.n_pad + n], kv, dec[r]);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
       }
-      // flush the last class segment
+      if (half == 1) {
 #pragma unroll
-      for (int cc = 0; cc < C; ++cc) {
-        if (cls == cc) {
-#pragma unroll
-          for (int r = 0; r < C - 1; ++r) {
-            const int o = (r < cc) ? r : r + 1;
-            const int lo = (cc < o) ? cc : o, hi = (cc < o) ? o : cc;
-            dec[lo * (2 * C - lo - 1) / 2 + (hi - lo - 1)] += acc[r];
-          }
-        }
+        for (int r = 0; r < NP; ++r) s_x[m * NP + r] = dec[r];
       }
-      if (b < p.B) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kK2EpiWarps * 32) : "memory");
+      if (half == 0 && b < p.B) {
 #pragma unroll
-        for (int r = 0; r < NP; ++r) dec[r] -= p.rho[r];
+        for (int r = 0; r < NP; ++r) dec[r] = dec[r] + s_x[m * NP + r] - p.rho[r];
         double f[C];
         ovr_transform<C>(dec, f);
         platt_argmax_store<C>(f, p.platt_a, p.platt_b, p.min_proba, b, p.proba, p.decision,
                               p.label, p.known);
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(kK2EpiWarps * 32) : "memory");
     }
   }
 

@@ -35,6 +35,7 @@ struct Model {
   int32_t* svnorm = nullptr;  // [n_sv]
   double* sv_f64 = nullptr;   // [n_sv][F]
   double* coef = nullptr;     // svc: [C-1][n_sv]; linear: [R][F]
+  double* pairw = nullptr;    // svc: [C(C-1)/2][n_pad] per-pair SV weights for the tensor-core scorer
   double* rho = nullptr;      // svc: [NP]; linear: intercept [R]
   double* platt_a = nullptr;
   double* platt_b = nullptr;
@@ -149,6 +150,7 @@ void free_model(Model& m) {
   cudaFree(m.svnorm);
   cudaFree(m.sv_f64);
   cudaFree(m.coef);
+  cudaFree(m.pairw);
   cudaFree(m.rho);
   cudaFree(m.platt_a);
   cudaFree(m.platt_b);
@@ -179,7 +181,9 @@ int encode_u8_map(rml_ctx* c, CUtensorMap* map, const void* base, int64_t rows, 
 
 template <int C>
 int launch_rbf_i8(rml_ctx* c, const CUtensorMap& map_feats, const K2Params& p, cudaStream_t st) {
-  const int smem = k2_smem_bytes(p.n_tile, p.stages);
+  const int smem = k2_smem_bytes(p.n_tile, p.stages, p.n_pad, C * (C - 1) / 2);
+  if (p.stages < 2)
+    return fail(c, RML_E_UNSUPPORTED, "k2_rbf_i8: %d support vectors x %d classes do not leave room for a 2-stage pipeline", p.n_sv, C);
   RML_CUDA(c, cudaFuncSetAttribute(k2_rbf_i8<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int64_t tiles = (p.B + kK2BlockM - 1) / kK2BlockM;
   const int grid = static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
@@ -287,8 +291,9 @@ int score_impl(rml_ctx* c, const void* feats, int dtype, const int32_t* norms, i
     if (rc) return rc;
     K2Params p;
     p.B = B; p.n_sv = m.n_sv; p.n_tile = m.n_tile; p.n_chunks = m.n_chunks; p.k_blocks = m.kpad / 128;
-    p.stages = k2_pick_stages(m.n_tile);
-    p.unorm = norms; p.svnorm = m.svnorm; p.coef = m.coef; p.rho = m.rho;
+    p.n_pad = m.n_tile * m.n_chunks;
+    p.stages = k2_pick_stages(m.n_tile, p.n_pad, m.C * (m.C - 1) / 2);
+    p.unorm = norms; p.svnorm = m.svnorm; p.pairw = m.pairw; p.rho = m.rho;
     p.platt_a = m.platt_a; p.platt_b = m.platt_b;
     p.neg_gamma_s2 = -m.gamma / (m.feature_scale * m.feature_scale);
     p.min_proba = min_proba; p.proba = proba; p.decision = decision; p.label = label; p.known = known;
@@ -459,7 +464,7 @@ int rml_load_svc_rbf(rml_ctx* c, int C, int F, int n_sv, const int32_t* n_suppor
   m.n_tile = round_up((n_sv + m.n_chunks - 1) / m.n_chunks, 16);
   const int n_pad = m.n_tile * m.n_chunks;
   std::vector<uint8_t> u8(static_cast<size_t>(n_pad) * m.kpad, 0);
-  std::vector<int32_t> norm(n_sv, 0);
+  std::vector<int32_t> norm(n_pad, 0);
   bool integral = true;
   for (int n = 0; n < n_sv && integral; ++n) {
     int64_t s2 = 0;
@@ -477,6 +482,20 @@ int rml_load_svc_rbf(rml_ctx* c, int C, int F, int n_sv, const int32_t* n_suppor
   m.integral = integral;
   int rc;
   if (integral) {
+    // weight of SV n (class cls) in OvO pair (i<j): dual_coef[j-1][n] if cls == i, dual_coef[i][n]
+    // if cls == j (svm.cpp:2864-2884), 0 otherwise; padded columns stay 0
+    const int NP = C * (C - 1) / 2;
+    std::vector<double> pw(static_cast<size_t>(NP) * n_pad, 0.0);
+    for (int n = 0, cls = 0; n < n_sv; ++n) {
+      while (n >= m.class_end[cls]) ++cls;
+      int pidx = 0;
+      for (int i = 0; i < C; ++i)
+        for (int j = i + 1; j < C; ++j, ++pidx) {
+          if (cls == i) pw[static_cast<size_t>(pidx) * n_pad + n] = dual_coef[static_cast<size_t>(j - 1) * n_sv + n];
+          else if (cls == j) pw[static_cast<size_t>(pidx) * n_pad + n] = dual_coef[static_cast<size_t>(i) * n_sv + n];
+        }
+    }
+    if ((rc = upload(c, &m.pairw, pw.data(), pw.size()))) return rc;
     if ((rc = upload(c, &m.sv_u8, u8.data(), u8.size()))) return rc;
     if ((rc = upload(c, &m.svnorm, norm.data(), norm.size()))) return rc;
     if ((rc = encode_u8_map(c, &m.map_sv, m.sv_u8, n_sv, F, m.kpad, m.n_tile))) return rc;
