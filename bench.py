@@ -148,7 +148,7 @@ def run_reference(args):
     from oracle import cpu_baseline, synth
     cores = cpu_baseline.host_cores()
     per_gpu = args.scans_per_gpu or (65536 if args.gpus == 1 else 131072)
-    sample = int(min(4096, max(256, 32 * cores)))
+    sample = 4096
     log("[reference] fitting model, generating %d sample scans on the host" % sample)
     cal = build_model()
     cubes, _, _ = synth.make_cubes(sample, seed=4321)
@@ -313,7 +313,7 @@ def run_ours(args):
                   "e2e_labels_equal": bool(np.array_equal(e2e_labels[:n_par], lab_o))}
         if world == 1:
             cores = cpu_baseline.host_cores()
-            sample = int(min(Be, 4096, max(256, 32 * cores)))
+            sample = int(min(Be, 4096))
             v, dt, used = cpu_baseline.run_all_cores(host_np[:sample], cal, synth.CLASSES, cores=cores)
             cpu = {"value": v, "unit": "scans/s", "cores": used, "kind": "port",
                    "sample": "%d of the GPU-scored scans, per-scan predict.py loop, one process per "
