@@ -204,6 +204,16 @@ int rml_net_predict(rml_ctx* ctx, const float* cubes_dev, int64_t B, int mode,
 /* ---- status of the last asynchronous work (non-integral count seen by the u8 path) ----- */
 int rml_check_status(rml_ctx* ctx, rml_stream stream); /* synchronises the stream */
 
+/* rml_predict runs K1 and K2 as ONE device-side pipeline for large batches: the projection
+ * kernel streams cubes on (SMs - k2_sms) SMs and counts finished scans per 128-scan tile; the
+ * scorer is co-resident on the other k2_sms SMs and starts a tile the moment it is complete.
+ * enabled=0 forces the serial K1 -> K2 order (also: env RML_FUSED=0, RML_K2_SMS, RML_FUSED_MIN_B). */
+int rml_set_fused(rml_ctx* ctx, int enabled, int k2_sms, int64_t min_batch);
+/* CUDA-event timing of the kernels inside the last rml_predict on this context: k1_ms =
+ * projection kernel alone, total_ms = projection start -> scorer end.  Synchronises. */
+int rml_enable_timing(rml_ctx* ctx, int enabled);
+int rml_last_timing(rml_ctx* ctx, float* k1_ms, float* total_ms, int* fused);
+
 /* number of kernels this library launched since create (bench.py "gpu_launches") */
 int64_t rml_launch_count(const rml_ctx* ctx);
 

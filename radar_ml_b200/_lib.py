@@ -95,6 +95,9 @@ SIGNATURES = {
     "rml_net_forward_images": (C.c_int, [_vp, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "rml_net_predict": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _sz, _vp, _vp, _vp]),
     "rml_check_status": (C.c_int, [_vp, _vp]),
+    "rml_set_fused": (C.c_int, [_vp, C.c_int, C.c_int, _i64]),
+    "rml_enable_timing": (C.c_int, [_vp, C.c_int]),
+    "rml_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "rml_launch_count": (_i64, [_vp]),
 }
 

@@ -6,9 +6,9 @@
 // filled by 1-D bulk async copies (UBLKCP) that complete on mbarriers.  Warp roles:
 //   warps 0..7  "row" warps: own 4 rows j of every slab; running max over i (yz) lives in
 //               registers, the per-row max over k (xy) is one CREDUX.MAX.F32 per row
-//   warps 8..9  "column" warps: alternate slabs, max over j for every k (xz)
-//   warp 10     producer: issues the bulk copies (one elected lane)
-//   warp 11     flusher: writes the finished feature row back (bulk S2G for u8)
+//   warps 8..11 "column" warps: every 4th slab each, max over j for every k (xz)
+//   warp 12     producer: issues the bulk copies (one elected lane)
+//   warp 13     flusher: writes the finished feature row back (bulk S2G for u8)
 // One HBM read of the cube, no re-reads; output is 2 % (u8) / 8 % (f32) of the input bytes.
 #pragma once
 #include <cfloat>
@@ -24,9 +24,17 @@ constexpr int kSlabElems = kSY * kSZ;              // 5456
 constexpr int kSlabBytes = kSlabElems * 4;         // 21824
 constexpr int kCubeElems = kSX * kSlabElems;       // 120032
 constexpr int kFxz = kSX * kSZ, kFyz = kSY * kSZ, kFxy = kSX * kSY;  // 3872, 5456, 682
-constexpr int kRowWarps = 8, kColWarps = 2;
-constexpr int kK1Threads = (kRowWarps + kColWarps + 2) * 32;  // 384
-constexpr int kK1Stages = 6;
+constexpr int kRowWarps = 8, kColWarps = 4;
+constexpr int kK1Threads = (kRowWarps + kColWarps + 2) * 32;  // 448
+// ring depth: 8 slabs (175 KB in flight) for the u8 path, 4 for f32 (its staging rows are 4x larger)
+template <typename OutT>
+struct K1Cfg {
+  static constexpr int kStages = sizeof(OutT) == 1 ? 8 : 4;
+};
+// A column warp only waits on the `full` barriers of the slabs it owns, so it must also own the
+// previous use of that ring slot (mbarrier parity waits cannot tell phase n from phase n-2).
+static_assert(K1Cfg<uint8_t>::kStages % kColWarps == 0 && K1Cfg<float>::kStages % kColWarps == 0,
+              "ring depth must be a multiple of the column-warp count");
 
 struct K1Params {
   const float* cubes;
@@ -39,6 +47,8 @@ struct K1Params {
   uint32_t mask;
   float offset, scale;  // f32 output: (v - offset) / scale when affine != 0
   int affine;
+  unsigned int* tile_done;  // nullable: [ceil(B/128)] += 1 per finished scan (u8 path) so a
+                            // co-resident scorer can start on a 128-scan tile as soon as it is whole
 };
 
 template <typename OutT>
@@ -89,11 +99,93 @@ __host__ __device__ constexpr int k1_staging_bytes() {
 }
 template <typename OutT>
 __host__ __device__ constexpr int k1_smem_bytes() {
-  return kK1Stages * kSlabBytes + 2 * k1_staging_bytes<OutT>() + 256;
+  return K1Cfg<OutT>::kStages * kSlabBytes + 2 * k1_staging_bytes<OutT>() + 256;
+}
+
+// Row-warp role of k1_project_max: NR rows j of every slab (NR compile-time so the 12 smem
+// loads of a slab are issued back to back and the NR warp reductions overlap).
+template <typename OutT, int NR>
+__device__ __forceinline__ void k1_row_warp(const K1Params& p, const float* slabs, OutT* stg0,
+                                            uint64_t* full, uint64_t* empty, uint64_t* done,
+                                            uint64_t* sfree, uint32_t* norm_acc, int warp, int lane) {
+  constexpr int kStgBytes = k1_staging_bytes<OutT>();
+  constexpr int kK1Stages = K1Cfg<OutT>::kStages;
+  const float NEG = -FLT_MAX;
+  const int off_yz = (p.mask & 1u) ? kFxz : 0;
+  const int off_xy = off_yz + ((p.mask & 2u) ? kFyz : 0);
+  const int j0 = warp * 4;
+  float yz[NR][6];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int m = 0; m < 6; ++m) yz[r][m] = NEG;
+  uint32_t sumsq = 0, bad = 0;
+  uint32_t it = 0, t = 0;
+  const bool third = lane < 24;
+  for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++t) {
+    const int buf = t & 1;
+    OutT* stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
+    mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
+    for (int i = 0; i < kSX; ++i, ++it) {
+      const int stage = it % kK1Stages;
+      mbar_wait(&full[stage], (it / kK1Stages) & 1);
+      const float2* rows = reinterpret_cast<const float2*>(slabs + stage * kSlabElems + j0 * kSZ);
+      float2 a[NR], c[NR], e[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        a[r] = rows[r * (kSZ / 2) + lane];
+        c[r] = rows[r * (kSZ / 2) + 32 + lane];
+        e[r] = third ? rows[r * (kSZ / 2) + 64 + lane] : make_float2(NEG, NEG);
+      }
+      float m[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        yz[r][0] = fmaxf(yz[r][0], a[r].x);
+        yz[r][1] = fmaxf(yz[r][1], a[r].y);
+        yz[r][2] = fmaxf(yz[r][2], c[r].x);
+        yz[r][3] = fmaxf(yz[r][3], c[r].y);
+        yz[r][4] = fmaxf(yz[r][4], e[r].x);
+        yz[r][5] = fmaxf(yz[r][5], e[r].y);
+        m[r] = fmaxf(fmaxf(fmaxf(a[r].x, a[r].y), fmaxf(c[r].x, c[r].y)), fmaxf(e[r].x, e[r].y));
+      }
+#pragma unroll
+      for (int r = 0; r < NR; ++r) m[r] = warp_max_f32(m[r]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);    // the slab has been consumed
+      // lane r stores the xy value of row r: one conversion per slab instead of NR
+      float mine = m[0];
+#pragma unroll
+      for (int r = 1; r < NR; ++r) mine = (lane == r) ? m[r] : mine;
+      if (lane < NR && (p.mask & 4u))
+        Emit<OutT>::put1(stg, off_xy + i * kSY + j0 + lane, mine, p, sumsq, bad);
+    }
+    // end of scan: the running max over i is the yz projection
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      if (p.mask & 2u) {
+        const int base = off_yz + (j0 + r) * kSZ + 2 * lane;
+        Emit<OutT>::put2(stg, base, yz[r][0], yz[r][1], p, sumsq, bad);
+        Emit<OutT>::put2(stg, base + 64, yz[r][2], yz[r][3], p, sumsq, bad);
+        if (third) Emit<OutT>::put2(stg, base + 128, yz[r][4], yz[r][5], p, sumsq, bad);
+      }
+#pragma unroll
+      for (int m2 = 0; m2 < 6; ++m2) yz[r][m2] = NEG;
+    }
+    if (sizeof(OutT) == 1) {
+      const uint32_t tot = __reduce_add_sync(0xffffffffu, sumsq);
+      if (lane == 0 && tot) atomicAdd(&norm_acc[buf], tot);
+      sumsq = 0;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&done[buf]);
+  }
+  if (bad) atomicAdd(p.status, 1u);
 }
 
 template <typename OutT>
 __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p) {
+  constexpr int kK1Stages = K1Cfg<OutT>::kStages;
   extern __shared__ __align__(128) unsigned char smem[];
   float* slabs = reinterpret_cast<float*>(smem);
   OutT* stg0 = reinterpret_cast<OutT*>(smem + kK1Stages * kSlabBytes);
@@ -135,69 +227,10 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
 
   if (warp < kRowWarps) {
     // ------------------------------------------------------------------ row warps
-    const int j0 = warp * 4;
-    const int nrows = (warp == kRowWarps - 1) ? (kSY - j0) : 4;
-    float yz[4][6];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int m = 0; m < 6; ++m) yz[r][m] = NEG;
-    uint32_t sumsq = 0, bad = 0;
-    for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++t) {
-      const int buf = t & 1;
-      OutT* stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
-      mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
-      for (int i = 0; i < kSX; ++i, ++it) {
-        const int stage = it % kK1Stages;
-        mbar_wait(&full[stage], (it / kK1Stages) & 1);
-        const float* slab = slabs + stage * kSlabElems;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          if (r < nrows) {
-            const float2* row = reinterpret_cast<const float2*>(slab + (j0 + r) * kSZ);
-            const float2 a = row[lane];
-            const float2 c = row[32 + lane];
-            float2 e = make_float2(NEG, NEG);
-            if (lane < 24) e = row[64 + lane];
-            yz[r][0] = fmaxf(yz[r][0], a.x);
-            yz[r][1] = fmaxf(yz[r][1], a.y);
-            yz[r][2] = fmaxf(yz[r][2], c.x);
-            yz[r][3] = fmaxf(yz[r][3], c.y);
-            yz[r][4] = fmaxf(yz[r][4], e.x);
-            yz[r][5] = fmaxf(yz[r][5], e.y);
-            float m = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(c.x, c.y)), fmaxf(e.x, e.y));
-            m = warp_max_f32(m);
-            if (lane == 0 && (p.mask & 4u))
-              Emit<OutT>::put1(stg, off_xy + i * kSY + j0 + r, m, p, sumsq, bad);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
-      }
-      // end of scan: the running max over i is the yz projection
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        if (r < nrows) {
-          if (p.mask & 2u) {
-            const int base = off_yz + (j0 + r) * kSZ + 2 * lane;
-            Emit<OutT>::put2(stg, base, yz[r][0], yz[r][1], p, sumsq, bad);
-            Emit<OutT>::put2(stg, base + 64, yz[r][2], yz[r][3], p, sumsq, bad);
-            if (lane < 24) Emit<OutT>::put2(stg, base + 128, yz[r][4], yz[r][5], p, sumsq, bad);
-          }
-#pragma unroll
-          for (int m = 0; m < 6; ++m) yz[r][m] = NEG;
-        }
-      }
-      if (sizeof(OutT) == 1) {
-        const uint32_t tot = __reduce_add_sync(0xffffffffu, sumsq);
-        if (lane == 0 && tot) atomicAdd(&norm_acc[buf], tot);
-        sumsq = 0;
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&done[buf]);
-    }
-    if (bad) atomicAdd(p.status, 1u);
+    if (warp == kRowWarps - 1)
+      k1_row_warp<OutT, kSY - 4 * (kRowWarps - 1)>(p, slabs, stg0, full, empty, done, sfree, norm_acc, warp, lane);
+    else
+      k1_row_warp<OutT, 4>(p, slabs, stg0, full, empty, done, sfree, norm_acc, warp, lane);
   } else if (warp < kRowWarps + kColWarps) {
     // ------------------------------------------------------------------ column warps
     const int c = warp - kRowWarps;
@@ -207,7 +240,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
       OutT* stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
       mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
       for (int i = 0; i < kSX; ++i, ++it) {
-        if ((i & 1) != c) continue;
+        if ((it % kColWarps) != static_cast<uint32_t>(c)) continue;   // ownership follows the ring slot
         const int stage = it % kK1Stages;
         mbar_wait(&full[stage], (it / kK1Stages) & 1);
         if (p.mask & 1u) {
@@ -273,6 +306,11 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
           norm_acc[buf] = 0;
           bulk_wait_read<0>();
           mbar_arrive(&sfree[buf]);
+          if (p.tile_done) {
+            bulk_wait_all<0>();          // the feature row has landed in global memory
+            __threadfence();
+            atomicAdd(&p.tile_done[b >> 7], 1u);
+          }
         }
       } else {
         // (n,F) float32 rows are only 8-byte aligned (F*4 = 40040): plain coalesced stores

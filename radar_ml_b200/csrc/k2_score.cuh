@@ -43,6 +43,7 @@ struct K2Params {
   const int32_t* svnorm;   // [n_pad] sum s^2 (n_pad = n_tile * n_chunks, zero padded)
   const double* pairw;     // [C(C-1)/2][n_pad] weight of SV n in OvO pair p (0 outside the pair)
   int n_pad;
+  const unsigned int* tile_ready;  // nullable: [tiles] scans of the tile finished by the producer kernel
   const double* rho;       // [C(C-1)/2]
   const double* platt_a;   // [C] (or [1] when C == 2)
   const double* platt_b;
@@ -218,6 +219,14 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
       const uint64_t pol_b = policy_evict_last();
       uint32_t kit = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (p.tile_ready) {
+          // fused pipeline: the projection kernel is still running on the other SMs; wait
+          // until every scan of this tile has its feature row in global memory
+          const int64_t left = p.B - tile * kK2BlockM;
+          const unsigned int need = left < kK2BlockM ? static_cast<unsigned int>(left) : kK2BlockM;
+          while (ld_acquire_gpu(&p.tile_ready[tile]) < need) __nanosleep(200);
+          fence_proxy_async_all();
+        }
         for (int ch = 0; ch < p.n_chunks; ++ch) {
           for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
             const int s = kit % kK2Stages;
@@ -272,6 +281,11 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
     uint32_t ait = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t b = tile * kK2BlockM + m;
+      if (p.tile_ready) {
+        const int64_t left = p.B - tile * kK2BlockM;
+        const unsigned int need = left < kK2BlockM ? static_cast<unsigned int>(left) : kK2BlockM;
+        while (ld_acquire_gpu(&p.tile_ready[tile]) < need) __nanosleep(200);
+      }
       const int un = (b < p.B) ? p.unorm[b] : 0;
       double dec[NP];
 #pragma unroll

@@ -5,7 +5,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <string>
 #include <vector>
 
@@ -93,6 +95,15 @@ struct rml_ctx {
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   HostPipe pipe;
   Net net;
+  // fused K1 || K2 pipeline: projection on most SMs, scorer co-resident on the rest
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_k1a = nullptr, ev_k1b = nullptr, ev_k2b = nullptr;
+  unsigned int* tile_done = nullptr;
+  int64_t tile_done_cap = 0;
+  int k2_sms = 32;           // SMs reserved for the scorer in fused mode (RML_K2_SMS); set from the SM count in rml_create
+  int64_t fused_min_b = 8192;
+  int fused_enabled = 1;     // RML_FUSED=0 disables
+  int last_fused = 0;
   // zoom operators (common.py:143 ndimage.zoom as separable matrices), per projection
   double* zoom_ar[3] = {nullptr, nullptr, nullptr};
   double* zoom_ac[3] = {nullptr, nullptr, nullptr};
@@ -180,13 +191,15 @@ int encode_u8_map(rml_ctx* c, CUtensorMap* map, const void* base, int64_t rows, 
 }
 
 template <int C>
-int launch_rbf_i8(rml_ctx* c, const CUtensorMap& map_feats, const K2Params& p, cudaStream_t st) {
+int launch_rbf_i8(rml_ctx* c, const CUtensorMap& map_feats, const K2Params& p, cudaStream_t st,
+                  int grid_limit) {
   const int smem = k2_smem_bytes(p.n_tile, p.stages, p.n_pad, C * (C - 1) / 2);
   if (p.stages < 2)
     return fail(c, RML_E_UNSUPPORTED, "k2_rbf_i8: %d support vectors x %d classes do not leave room for a 2-stage pipeline", p.n_sv, C);
   RML_CUDA(c, cudaFuncSetAttribute(k2_rbf_i8<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int64_t tiles = (p.B + kK2BlockM - 1) / kK2BlockM;
-  const int grid = static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
+  const int sms = grid_limit > 0 ? grid_limit : c->num_sms;
+  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
   k2_rbf_i8<C><<<grid, kK2Threads, smem, st>>>(map_feats, c->model.map_sv, p);
   RML_CUDA(c, cudaGetLastError());
   ++c->launches;
@@ -220,7 +233,8 @@ int launch_linear(rml_ctx* c, const K2LinParams& p, cudaStream_t st) {
   }
 
 int project_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int32_t* ijk,
-                 uint32_t mask, int dtype, void* feats, int32_t* norms, cudaStream_t st) {
+                 uint32_t mask, int dtype, void* feats, int32_t* norms, cudaStream_t st,
+                 int grid_limit = 0, unsigned int* tile_done = nullptr) {
   if (B < 0 || !cubes || !feats) return fail(c, RML_E_INVALID, "rml_project: null buffer or B<0");
   if ((mask & RML_MASK_ALL) == 0 || (mask & ~RML_MASK_ALL))
     return fail(c, RML_E_INVALID, "rml_project: mask %u selects no projection", mask);
@@ -238,7 +252,9 @@ int project_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
     p.cubes = cubes; p.feats = feats; p.norms = norms; p.status = c->status; p.B = B;
     p.stride = stride; p.F = F; p.mask = mask;
     p.offset = c->aff_offset; p.scale = c->aff_scale; p.affine = c->aff_enabled;
-    const int grid = static_cast<int>(B < c->num_sms ? B : c->num_sms);
+    p.tile_done = dtype == RML_U8 ? tile_done : nullptr;
+    const int sms = grid_limit > 0 ? grid_limit : c->num_sms;
+    const int grid = static_cast<int>(B < sms ? B : sms);
     if (dtype == RML_U8) {
       const int smem = k1_smem_bytes<uint8_t>();
       RML_CUDA(c, cudaFuncSetAttribute(k1_project_max<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -265,7 +281,7 @@ int project_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
 
 int score_impl(rml_ctx* c, const void* feats, int dtype, const int32_t* norms, int64_t B,
                double min_proba, float* proba, float* decision, int32_t* label, uint8_t* known,
-               cudaStream_t st) {
+               cudaStream_t st, int grid_limit = 0, const unsigned int* tile_ready = nullptr) {
   Model& m = c->model;
   if (m.kind == 0) return fail(c, RML_E_NOMODEL, "rml_score: no model loaded");
   if (!feats || !proba || !label || B < 0) return fail(c, RML_E_INVALID, "rml_score: null buffer or B<0");
@@ -298,7 +314,8 @@ int score_impl(rml_ctx* c, const void* feats, int dtype, const int32_t* norms, i
     p.neg_gamma_s2 = -m.gamma / (m.feature_scale * m.feature_scale);
     p.min_proba = min_proba; p.proba = proba; p.decision = decision; p.label = label; p.known = known;
     for (int i = 0; i < kMaxClasses; ++i) p.class_end[i] = m.class_end[i];
-    DISPATCH_C(m.C, launch_rbf_i8<CC>(c, map_feats, p, st));
+    p.tile_ready = tile_ready;
+    DISPATCH_C(m.C, launch_rbf_i8<CC>(c, map_feats, p, st, grid_limit));
   }
   K2GenParams p;
   p.B = B; p.F = m.F; p.n_sv = m.n_sv; p.feats = static_cast<const float*>(feats); p.sv = m.sv_f64;
@@ -331,10 +348,50 @@ int predict_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
   const float so = c->aff_offset, ss = c->aff_scale;
   // the scorer expects features scaled like common.process_samples(scale=True)
   c->aff_enabled = 1; c->aff_offset = 0.f; c->aff_scale = static_cast<float>(c->model.feature_scale);
+  const bool fused = c->fused_enabled && c->model.kind == 1 && dtype == RML_U8 && mode == RML_MODE_MAX &&
+                     c->sx == kSX && c->sy == kSY && c->sz == kSZ && B >= c->fused_min_b &&
+                     c->k2_sms > 0 && c->k2_sms < c->num_sms;
+  c->last_fused = fused ? 1 : 0;
+  if (fused) {
+    // One pipeline, two co-resident kernels: K1 streams cubes on (num_sms - k2_sms) SMs and
+    // bumps a per-tile counter for every finished scan; K2 runs on the remaining SMs and
+    // starts on a 128-scan tile as soon as its counter is full (device-side flags, no host sync).
+    const int64_t tiles = (B + kK2BlockM - 1) / kK2BlockM;
+    if (!c->aux_stream) {
+      RML_CUDA(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+      RML_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+      RML_CUDA(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    if (c->tile_done_cap < tiles) {
+      cudaFree(c->tile_done);
+      RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->tile_done), tiles * sizeof(unsigned int)));
+      c->tile_done_cap = tiles;
+    }
+    RML_CUDA(c, cudaMemsetAsync(c->tile_done, 0, tiles * sizeof(unsigned int), st));
+    RML_CUDA(c, cudaEventRecord(c->ev_fork, st));
+    RML_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+    if (c->ev_k1a) RML_CUDA(c, cudaEventRecord(c->ev_k1a, st));
+    int rc = project_impl(c, cubes, B, mode, ijk, mask, dtype, work, norms, st,
+                          c->num_sms - c->k2_sms, c->tile_done);
+    if (c->ev_k1b) RML_CUDA(c, cudaEventRecord(c->ev_k1b, st));
+    c->aff_enabled = saved; c->aff_offset = so; c->aff_scale = ss;
+    if (rc) return rc;
+    rc = score_impl(c, work, dtype, norms, B, min_proba, proba, nullptr, label, known, c->aux_stream,
+                    c->k2_sms, c->tile_done);
+    if (rc) return rc;
+    RML_CUDA(c, cudaEventRecord(c->ev_join, c->aux_stream));
+    RML_CUDA(c, cudaStreamWaitEvent(st, c->ev_join, 0));
+    if (c->ev_k2b) RML_CUDA(c, cudaEventRecord(c->ev_k2b, st));
+    return RML_OK;
+  }
+  if (c->ev_k1a) RML_CUDA(c, cudaEventRecord(c->ev_k1a, st));
   int rc = project_impl(c, cubes, B, mode, ijk, mask, dtype, work, norms, st);
+  if (c->ev_k1b) RML_CUDA(c, cudaEventRecord(c->ev_k1b, st));
   c->aff_enabled = saved; c->aff_offset = so; c->aff_scale = ss;
   if (rc) return rc;
-  return score_impl(c, work, dtype, norms, B, min_proba, proba, nullptr, label, known, st);
+  rc = score_impl(c, work, dtype, norms, B, min_proba, proba, nullptr, label, known, st);
+  if (c->ev_k2b && rc == RML_OK) RML_CUDA(c, cudaEventRecord(c->ev_k2b, st));
+  return rc;
 }
 
 void free_net(Net& n) {
@@ -397,6 +454,11 @@ int rml_create(int device, rml_ctx** out) {
     delete c;
     return fail(nullptr, RML_E_CUDA, "status allocation failed");
   }
+  // measured optimum on B200 (148 SMs): 32 scorer SMs, 116 projection SMs (profiles/r1_fused_sweep.txt)
+  c->k2_sms = (c->num_sms * 32 + 74) / 148;
+  if (const char* e1 = getenv("RML_K2_SMS")) c->k2_sms = atoi(e1);
+  if (const char* e2 = getenv("RML_FUSED")) c->fused_enabled = atoi(e2);
+  if (const char* e3 = getenv("RML_FUSED_MIN_B")) c->fused_min_b = atoll(e3);
   *out = c;
   return RML_OK;
 }
@@ -407,6 +469,10 @@ int rml_destroy(rml_ctx* c) {
   cudaDeviceSynchronize();
   free_model(c->model);
   free_pipe(c->pipe);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  for (cudaEvent_t e : {c->ev_fork, c->ev_join, c->ev_k1a, c->ev_k1b, c->ev_k2b})
+    if (e) cudaEventDestroy(e);
+  cudaFree(c->tile_done);
   free_net(c->net);
   for (int q = 0; q < 3; ++q) { cudaFree(c->zoom_ar[q]); cudaFree(c->zoom_ac[q]); }
   cudaFree(c->status);
@@ -690,6 +756,39 @@ int rml_check_status(rml_ctx* c, rml_stream stream) {
 }
 
 int64_t rml_launch_count(const rml_ctx* c) { return c ? c->launches : 0; }
+
+int rml_enable_timing(rml_ctx* c, int enabled) {
+  if (!c) return RML_E_INVALID;
+  DeviceGuard g(c->device);
+  if (enabled && !c->ev_k1a) {
+    RML_CUDA(c, cudaEventCreate(&c->ev_k1a));
+    RML_CUDA(c, cudaEventCreate(&c->ev_k1b));
+    RML_CUDA(c, cudaEventCreate(&c->ev_k2b));
+  } else if (!enabled && c->ev_k1a) {
+    cudaEventDestroy(c->ev_k1a); cudaEventDestroy(c->ev_k1b); cudaEventDestroy(c->ev_k2b);
+    c->ev_k1a = c->ev_k1b = c->ev_k2b = nullptr;
+  }
+  return RML_OK;
+}
+
+int rml_last_timing(rml_ctx* c, float* k1_ms, float* total_ms, int* fused) {
+  if (!c) return RML_E_INVALID;
+  if (!c->ev_k1a) return fail(c, RML_E_INVALID, "rml_last_timing: call rml_enable_timing first");
+  DeviceGuard g(c->device);
+  RML_CUDA(c, cudaEventSynchronize(c->ev_k2b));
+  if (k1_ms) RML_CUDA(c, cudaEventElapsedTime(k1_ms, c->ev_k1a, c->ev_k1b));
+  if (total_ms) RML_CUDA(c, cudaEventElapsedTime(total_ms, c->ev_k1a, c->ev_k2b));
+  if (fused) *fused = c->last_fused;
+  return RML_OK;
+}
+
+int rml_set_fused(rml_ctx* c, int enabled, int k2_sms, int64_t min_batch) {
+  if (!c) return RML_E_INVALID;
+  c->fused_enabled = enabled;
+  if (k2_sms > 0) c->k2_sms = k2_sms;
+  if (min_batch > 0) c->fused_min_b = min_batch;
+  return RML_OK;
+}
 
 
 // ------------------------------------------------------------------------------ §8f callers
