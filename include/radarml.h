@@ -180,6 +180,10 @@ int rml_net_set_dense(rml_ctx* ctx, int K, const uint16_t* w1t_bf16_host, const 
                       int act1, const float* w2_host, const float* b2_host, int act2,
                       const float* w3_host, const float* b3_host);
 int rml_net_finish(rml_ctx* ctx);
+/* 1 when the conv layers after the first run as tcgen05 implicit GEMMs on bf16 activations
+ * (every such layer has Cin % 64 == 0, Cout % 16 == 0, Cout <= 128); env RML_IGEMM=0 forces the
+ * fp32 CUDA-core towers. */
+int rml_net_uses_igemm(const rml_ctx* ctx);
 size_t rml_net_workspace_bytes(const rml_ctx* ctx, int64_t chunk_scans);
 /* feats_dev: float32 [B][10010] projections scaled (p-127.5)/127.5 (rml_project with
  * rml_set_affine(127.5, 127.5, 1)).  The batch is processed in chunks that fit the workspace.

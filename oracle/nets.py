@@ -210,16 +210,36 @@ def conv3x3_s2_same(x: np.ndarray, w: np.ndarray, b: np.ndarray) -> np.ndarray:
     return out + np.asarray(b, dtype=np.float64)
 
 
-def tower_output(net: NetParams, X: np.ndarray) -> np.ndarray:
+def _fold(layer, eps):
+    w = np.asarray(layer.w, dtype=np.float64)
+    b = np.asarray(layer.b, dtype=np.float64)
+    if layer.bn is None:
+        return w, b
+    g, beta, m, v = (np.asarray(t, dtype=np.float64) for t in layer.bn)
+    s = g / np.sqrt(v + eps)
+    return w * s, (b - m) * s + beta
+
+
+def tower_output(net: NetParams, X: np.ndarray, bf16_towers: bool = False) -> np.ndarray:
     """Conv towers only: (n, R, R, 3) -> float64 (n, 3, h, w, c) in the device's
-    [branch][h][w][c] order (before any bf16 rounding)."""
+    [branch][h][w][c] order.  bf16_towers=True reproduces the rounding points of the
+    tensor-core towers: every layer's output activation is rounded to bf16 and the kernels of
+    the layers after the first (BatchNorm folded, as on the device) are rounded to bf16."""
     X = np.asarray(X, dtype=np.float64)
     outs = []
     for br in range(3):
         h = X[:, :, :, br:br + 1]
-        for layer in net.branches[br]:
-            h = conv3x3_s2_same(h, layer.w, layer.b)
-            h = _act(_bn_apply(h, layer.bn, net.bn_eps), layer.act, net.alpha)
+        for li, layer in enumerate(net.branches[br]):
+            if bf16_towers:
+                w, b = _fold(layer, net.bn_eps)
+                if li >= 1:
+                    w = bf16_round(w)
+                h = _act(conv3x3_s2_same(h, w, b), layer.act, net.alpha)
+                if li + 1 < len(net.branches[br]):
+                    h = bf16_round(h)
+            else:
+                h = conv3x3_s2_same(h, layer.w, layer.b)
+                h = _act(_bn_apply(h, layer.bn, net.bn_eps), layer.act, net.alpha)
         outs.append(h)
     return np.stack(outs, axis=1)
 
@@ -250,6 +270,12 @@ def dense_from_tower(net: NetParams, tower: np.ndarray):
 
 def bf16_bits_to_float(bits: np.ndarray) -> np.ndarray:
     return (np.asarray(bits).astype(np.uint16).astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+
+
+def forward_bf16_towers(net: NetParams, X: np.ndarray):
+    """Whole network with every rounding point of the tensor-core path (towers + dense)."""
+    t = tower_output(net, X, bf16_towers=True)
+    return dense_from_tower(net, bf16_round(t))
 
 
 def forward(net: NetParams, X: np.ndarray, bf16_points: bool = False):

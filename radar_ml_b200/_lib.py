@@ -89,6 +89,7 @@ SIGNATURES = {
     "rml_net_add_conv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rml_net_set_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp]),
     "rml_net_finish": (C.c_int, [_vp]),
+    "rml_net_uses_igemm": (C.c_int, [_vp]),
     "rml_net_workspace_bytes": (_sz, [_vp, _i64]),
     "rml_net_forward": (C.c_int, [_vp, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp]),
     "rml_net_resize": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),

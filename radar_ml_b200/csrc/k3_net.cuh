@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) k3_resize_pil(const ResizeParams p) {
 // ------------------------------------------------------------------------------ K4 conv
 constexpr int kConvCoutTile = 32;
 struct ConvParams {
-  const float* in;        // [n_img][H][W][Cin]   (n_img = scans * 3, branch = img % 3)
+  const float* in;        // [n_img][H][W][Cin] fp32 (n_img = scans * 3, branch = img % 3)
   void* out;              // [n_img][Ho][Wo][Cout] fp32 or bf16
   const float* w[3];      // per branch [3][3][Cin][Cout] (Keras HWIO, BN folded)
   const float* bias[3];   // per branch [Cout]
@@ -167,6 +167,240 @@ __global__ void __launch_bounds__(256) k4_conv3x3s2(const ConvParams p) {
                         apply_act(acc[c + 2], p.act, p.alpha), apply_act(acc[c + 3], p.act, p.alpha));
     }
   }
+}
+
+// First tower layer (Cin = 1, K = 9): a lane owns CPL = Cout/32 output channels with its 9*CPL
+// weights in registers and walks over pixels; the 9 input taps are warp-uniform loads and every
+// pixel is written as one fully coalesced Cout*2-byte bf16 row.  Bound by the activation write.
+struct Conv1Params {
+  const float* in;        // [n_img][H][W] fp32 (single channel)
+  __nv_bfloat16* out;     // [n_img][Ho][Wo][Cout]
+  const float* w[3];      // per branch [9][Cout]
+  const float* bias[3];
+  int64_t n_img;
+  int H, W, Cout, Ho, Wo, pad_t, pad_l;
+  int act;
+  float alpha;
+};
+constexpr int kConv1Run = 64;   // pixels per warp task
+
+template <int CPL>
+__global__ void __launch_bounds__(256) k4_conv1_cin1(const Conv1Params p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int npix = p.Ho * p.Wo;
+  const int runs = (npix + kConv1Run - 1) / kConv1Run;
+  const int64_t tasks = p.n_img * runs;
+  int cur_br = -1;
+  float w[9][CPL], bs[CPL];
+  for (int64_t task = warp_global; task < tasks; task += n_warps) {
+    const int64_t img = task / runs;
+    const int run = static_cast<int>(task - img * runs);
+    const int br = static_cast<int>(img % 3);
+    if (br != cur_br) {
+      cur_br = br;
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) w[t][c] = p.w[br][t * p.Cout + lane * CPL + c];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) bs[c] = p.bias[br][lane * CPL + c];
+    }
+    const float* in = p.in + img * static_cast<int64_t>(p.H) * p.W;
+    __nv_bfloat16* out = p.out + img * static_cast<int64_t>(npix) * p.Cout + lane * CPL;
+    const int p0 = run * kConv1Run;
+    const int p1 = p0 + kConv1Run < npix ? p0 + kConv1Run : npix;
+    for (int px = p0; px < p1; ++px) {
+      const int oy = px / p.Wo, ox = px - oy * p.Wo;
+      float acc[CPL];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) acc[c] = bs[c];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int iy = oy * 2 + kh - p.pad_t;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ix = ox * 2 + kw - p.pad_l;
+          float x = 0.f;
+          if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) x = __ldg(in + iy * p.W + ix);
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) acc[c] = fmaf(x, w[kh * 3 + kw][c], acc[c]);
+        }
+      }
+      __nv_bfloat16* o = out + static_cast<int64_t>(px) * p.Cout;
+#pragma unroll
+      for (int c = 0; c < CPL; c += 2)
+        *reinterpret_cast<__nv_bfloat162*>(o + c) =
+            __floats2bfloat162_rn(apply_act(acc[c], p.act, p.alpha), apply_act(acc[c + 1], p.act, p.alpha));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ K4 implicit GEMM
+// Conv2D(3x3, strides 2, 'same') for Cin % 64 == 0 as a tcgen05 implicit GEMM:
+//   M = 128 output pixels (a TH x Wo block of one image), N = Cout, K = 9 taps x Cin.
+// The im2col operand is never materialised: for tap (kh,kw) and channel block cb the A tile is
+// ONE 4-D tiled TMA load of the NHWC bf16 activation with element strides (1,2,2,1) — box
+// {64 ch, 2*Wo, 2*TH, 1} starting at (cb*64, kw - pad, 2*oy0 + kh - pad, img) — which lands as
+// TH*Wo rows of 128 B in the 128B-swizzled K-major layout UMMA reads; out-of-image taps are
+// zero-filled by the TMA unit (TF 'same': the extra padding is after).  Weights [3*Cout][9*Cin]
+// bf16 come through a 2-D map.  Same warp roles as k5_dense_stack; the epilogue adds the bias,
+// applies ReLU / LeakyReLU and writes NHWC bf16.
+constexpr int kCgThreads = 192;
+constexpr int kCgStages = 6;
+struct ConvGemmParams {
+  int64_t n_img;
+  int Ho, Wo, Cin, Cout;
+  int TH;                 // output rows per tile (TH * Wo <= 128)
+  int tiles_per_img;
+  int pad_t, pad_l;
+  int act;
+  float alpha;
+  const float* bias;      // [3][Cout]
+  __nv_bfloat16* out;     // [n_img][Ho][Wo][Cout]
+};
+__host__ __device__ constexpr int cg_stage_bytes(int cout) { return 128 * 128 + cout * 128; }
+__host__ __device__ constexpr int cg_smem_bytes(int cout) {
+  return kCgStages * cg_stage_bytes(cout) + 1024 + 256 + 3 * 128 * 4;
+}
+
+__global__ void __launch_bounds__(kCgThreads, 1)
+k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+              const ConvGemmParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int stage_bytes = cg_stage_bytes(p.Cout);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCgStages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kCgStages;
+  uint64_t* tfull = empty + kCgStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + kCgStages * stage_bytes + 256);   // [3][Cout<=128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_tiles = p.n_img * p.tiles_per_img;
+  const int cblocks = p.Cin / 64;
+  const int k_blocks = 9 * cblocks;
+  const int a_bytes = p.TH * p.Wo * 128;
+
+  for (int e = threadIdx.x; e < 3 * p.Cout; e += blockDim.x) s_bias[e] = p.bias[e];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kCgStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol_a = policy_evict_last();    // every activation pixel is read ~2.25 times
+      const uint64_t pol_b = policy_evict_last();
+      uint32_t kit = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t img = tile / p.tiles_per_img;
+        const int tb = static_cast<int>(tile - img * p.tiles_per_img);
+        int oy0 = tb * p.TH;
+        if (oy0 > p.Ho - p.TH) oy0 = p.Ho - p.TH;        // last block overlaps instead of being ragged
+        const int br = static_cast<int>(img % 3);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int kh = tap / 3, kw = tap - kh * 3;
+          for (int cb = 0; cb < cblocks; ++cb, ++kit) {
+            const int s = kit % kCgStages;
+            mbar_wait(&empty[s], ((kit / kCgStages) & 1) ^ 1);
+            unsigned char* a_dst = smem + s * stage_bytes;
+            unsigned char* b_dst = a_dst + 128 * 128;
+            mbar_arrive_expect_tx(&full[s], a_bytes + p.Cout * 128);
+            tma_load_4d(a_dst, &map_x, cb * 64, kw - p.pad_l, 2 * oy0 + kh - p.pad_t,
+                        static_cast<int32_t>(img), &full[s], pol_a);
+            tma_load_2d(b_dst, &map_w, (tap * cblocks + cb) * 64, br * p.Cout, &full[s], pol_b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(kCF32, kFmtBF16, kFmtBF16, 128, p.Cout);
+      uint32_t kit = 0, ait = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ait) {
+        const int ab = ait & 1;
+        mbar_wait(&tempty[ab], ((ait >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * 128;
+        for (int kb = 0; kb < k_blocks; ++kb, ++kit) {
+          const int s = kit % kCgStages;
+          mbar_wait(&full[s], (kit / kCgStages) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint32_t b_addr = a_addr + 128 * 128;
+          const uint64_t da = umma_desc_k_sw128(a_addr);
+          const uint64_t db = umma_desc_k_sw128(b_addr);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(d_tmem, da + (ks * 32 >> 4), db + (ks * 32 >> 4), idesc, (kb | ks) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[ab]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int r = m / p.Wo, cx = m - r * p.Wo;
+    const bool valid = r < p.TH;
+    uint32_t ait = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ait) {
+      const int ab = ait & 1;
+      const int64_t img = tile / p.tiles_per_img;
+      const int tb = static_cast<int>(tile - img * p.tiles_per_img);
+      int oy0 = tb * p.TH;
+      if (oy0 > p.Ho - p.TH) oy0 = p.Ho - p.TH;
+      const float* bias = s_bias + (img % 3) * p.Cout;
+      mbar_wait(&tfull[ab], (ait >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ab * 128 + (static_cast<uint32_t>(q * 32) << 16);
+      __nv_bfloat16* out = p.out + ((img * p.Ho + oy0 + r) * p.Wo + cx) * p.Cout;
+      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const float a0 = apply_act(__uint_as_float(v[e]) + bias[c0 + e], p.act, p.alpha);
+            const float a1 = apply_act(__uint_as_float(v[e + 1]) + bias[c0 + e + 1], p.act, p.alpha);
+            __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+            pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(out + c0);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[ab]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
 // ------------------------------------------------------------------------------ K5 dense stack

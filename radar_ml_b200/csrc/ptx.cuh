@@ -90,6 +90,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
       "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+// 4-D tiled TMA load (NHWC activations, strided boxes for the implicit-GEMM convolution).
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* map, int32_t c0,
+                                            int32_t c1, int32_t c2, int32_t c3, uint64_t* bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%2, %3, %4, %5}], [%6], %7;" ::"r"(smem_u32(dst_smem)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

@@ -62,9 +62,14 @@ struct NetConv {
   int cin = 0, cout = 0, act = 0;
   float* w[3] = {nullptr, nullptr, nullptr};
   float* bias[3] = {nullptr, nullptr, nullptr};
+  std::vector<float> w_host[3], b_host[3];   // kept for the implicit-GEMM repack at finish
+  uint16_t* wt_bf16 = nullptr;               // [3*cout][9*cin] bf16, K = tap*cin + ci
+  float* bias3 = nullptr;                    // [3][cout]
+  CUtensorMap map_w;
 };
 struct Net {
   bool ready = false;
+  bool use_igemm = false;   // layers >= 1 run as tcgen05 implicit GEMMs on bf16 activations
   int R = 0, C = 0, head = 0;
   float alpha = 0.2f;
   std::vector<NetConv> convs;
@@ -395,8 +400,10 @@ int predict_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
 }
 
 void free_net(Net& n) {
-  for (auto& cv : n.convs)
+  for (auto& cv : n.convs) {
     for (int b = 0; b < 3; ++b) { cudaFree(cv.w[b]); cudaFree(cv.bias[b]); }
+    cudaFree(cv.wt_bf16); cudaFree(cv.bias3);
+  }
   cudaFree(n.w1t); cudaFree(n.b1); cudaFree(n.w2); cudaFree(n.b2); cudaFree(n.w3); cudaFree(n.b3);
   for (int b = 0; b < 3; ++b) { cudaFree(n.kh[b]); cudaFree(n.kv[b]); cudaFree(n.bh[b]); cudaFree(n.bv[b]); }
   n = Net();
@@ -922,6 +929,8 @@ int rml_net_add_conv(rml_ctx* c, int layer, int branch, int cin, int cout, int a
   int rc;
   if ((rc = upload(c, &cv.w[branch], w_hwio, static_cast<size_t>(9) * cin * cout))) return rc;
   if ((rc = upload(c, &cv.bias[branch], bias, static_cast<size_t>(cout)))) return rc;
+  cv.w_host[branch].assign(w_hwio, w_hwio + static_cast<size_t>(9) * cin * cout);
+  cv.b_host[branch].assign(bias, bias + cout);
   return RML_OK;
 }
 
@@ -982,11 +991,53 @@ int rml_net_finish(rml_ctx* c) {
   DeviceGuard g(c->device);
   int rc = encode_bf16_map(c, &n.map_w1, n.w1t, 64, n.K, 64);
   if (rc) return rc;
+  // tensor-core implicit GEMM for every layer after the first when the shapes allow it
+  bool ok = n.convs.size() >= 2;
+  {
+    int hw = n.R;
+    for (size_t l = 0; l < n.convs.size(); ++l) {
+      const NetConv& cv = n.convs[l];
+      const int ho = (hw + 1) / 2;
+      if (l >= 1 && (cv.cin % 64 || cv.cout % 16 || cv.cout > 128 || ho > 128 || (hw & 1))) ok = false;
+      hw = ho;
+    }
+  }
+  if (const char* e = getenv("RML_IGEMM")) ok = ok && atoi(e) != 0;
+  n.use_igemm = ok;
+  if (ok) {
+    for (size_t l = 1; l < n.convs.size(); ++l) {
+      NetConv& cv = n.convs[l];
+      const int K = 9 * cv.cin;
+      std::vector<uint16_t> wt(static_cast<size_t>(3) * cv.cout * K);
+      std::vector<float> b3(static_cast<size_t>(3) * cv.cout);
+      for (int br = 0; br < 3; ++br) {
+        for (int co = 0; co < cv.cout; ++co) {
+          b3[br * cv.cout + co] = cv.b_host[br][co];
+          for (int tap = 0; tap < 9; ++tap)
+            for (int ci = 0; ci < cv.cin; ++ci) {
+              const float v = cv.w_host[br][(static_cast<size_t>(tap) * cv.cin + ci) * cv.cout + co];
+              uint32_t u;
+              memcpy(&u, &v, 4);
+              u = (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;      // round to nearest even
+              wt[(static_cast<size_t>(br) * cv.cout + co) * K + tap * cv.cin + ci] = static_cast<uint16_t>(u);
+            }
+        }
+      }
+      if ((rc = upload(c, &cv.wt_bf16, wt.data(), wt.size()))) return rc;
+      if ((rc = upload(c, &cv.bias3, b3.data(), b3.size()))) return rc;
+      if ((rc = encode_bf16_map(c, &cv.map_w, cv.wt_bf16, 3 * cv.cout, K, cv.cout))) return rc;
+    }
+  }
   n.ready = true;
   return RML_OK;
 }
 
-static size_t net_core_bytes_per_scan(const rml_ctx* c) {
+// Workspace plan of the network forward:
+//   [ tower chunk: images | ping | pong ] [ flat bf16 tower output of a dense group ] [ f32 features of a chunk ]
+// The conv towers run chunk by chunk (their activations are large); the tcgen05 dense stack runs
+// once per dense group of up to kDenseGroup scans so that it has >= 128 tiles to spread over the SMs.
+constexpr int64_t kDenseGroup = 16384;
+static size_t net_tower_bytes_per_scan(const rml_ctx* c) {
   const Net& n = c->net;
   size_t img = static_cast<size_t>(3) * n.R * n.R * 4;
   size_t act = 0;
@@ -996,17 +1047,44 @@ static size_t net_core_bytes_per_scan(const rml_ctx* c) {
     size_t a = static_cast<size_t>(3) * hw * hw * n.convs[l].cout * 4;
     if (a > act) act = a;
   }
-  // images | two ping-pong fp32 activation buffers | bf16 flattened tower output
-  return img + 2 * act + static_cast<size_t>(n.K) * 2;
+  return img + 2 * act;
 }
-static size_t net_bytes_per_scan(const rml_ctx* c) {
-  // ... | f32 features of the chunk (rml_net_predict only)
-  return net_core_bytes_per_scan(c) + static_cast<size_t>(feature_len(c, RML_MASK_ALL)) * 4;
+struct NetPlan {
+  int64_t chunk = 0, group = 0;
+  size_t flat_off = 0, feats_off = 0;
+};
+static size_t net_plan_bytes(const rml_ctx* c, int64_t chunk, int64_t group) {
+  const size_t F4 = static_cast<size_t>(feature_len(c, RML_MASK_ALL)) * 4;
+  return align256(net_tower_bytes_per_scan(c) * chunk + 1024) + align256(static_cast<size_t>(group) * c->net.K * 2) +
+         align256(F4 * chunk) + 1024;
 }
+static int net_make_plan(rml_ctx* c, int64_t B, size_t ws_bytes, NetPlan* pl) {
+  int64_t group = B < kDenseGroup ? B : kDenseGroup;
+  for (;;) {
+    const size_t flat = align256(static_cast<size_t>(group) * c->net.K * 2);
+    const size_t F4 = static_cast<size_t>(feature_len(c, RML_MASK_ALL)) * 4;
+    const size_t per = net_tower_bytes_per_scan(c) + F4;
+    if (ws_bytes > flat + 4096 + per) {
+      int64_t chunk = static_cast<int64_t>((ws_bytes - flat - 4096) / per);
+      if (chunk > group) chunk = group;
+      if (chunk >= 1) {
+        pl->chunk = chunk; pl->group = group;
+        pl->flat_off = align256(net_tower_bytes_per_scan(c) * chunk + 1024);
+        pl->feats_off = pl->flat_off + flat;
+        return RML_OK;
+      }
+    }
+    if (group <= 128) break;
+    group /= 2;
+  }
+  return fail(c, RML_E_INVALID, "network workspace too small: %zu bytes", ws_bytes);
+}
+
+int rml_net_uses_igemm(const rml_ctx* c) { return c && c->net.ready && c->net.use_igemm; }
 
 size_t rml_net_workspace_bytes(const rml_ctx* c, int64_t chunk) {
   if (!c || !c->net.ready || chunk <= 0) return 0;
-  return net_bytes_per_scan(c) * static_cast<size_t>(chunk) + 4096;
+  return net_plan_bytes(c, chunk, kDenseGroup);
 }
 
 static int net_resize(rml_ctx* c, const float* feats, int64_t n_scans, float* images, cudaStream_t st) {
@@ -1031,10 +1109,10 @@ static int net_resize(rml_ctx* c, const float* feats, int64_t n_scans, float* im
   return RML_OK;
 }
 
-// feats != null: K3 resize into the workspace first; else images_in [n][3][R][R] is used as is
-static int net_forward_chunk(rml_ctx* c, const float* feats, const float* images_in, int64_t n_scans,
-                             char* ws, float* proba, float* logits, int32_t* label, cudaStream_t st,
-                             uint16_t* flat_out = nullptr) {
+// Towers of one chunk -> flat (bf16 [n_scans][K]).  feats != null: K3 resize into the workspace
+// first; else images_in [n][3][R][R] is used as is.
+static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_in, int64_t n_scans,
+                            char* ws, uint16_t* flat, cudaStream_t st) {
   Net& n = c->net;
   size_t img_b = align256(static_cast<size_t>(n_scans) * 3 * n.R * n.R * 4);
   size_t act = 0;
@@ -1050,40 +1128,85 @@ static int net_forward_chunk(rml_ctx* c, const float* feats, const float* images
   float* images = reinterpret_cast<float*>(ws);
   float* ping = reinterpret_cast<float*>(ws + img_b);
   float* pong = reinterpret_cast<float*>(ws + img_b + act_b);
-  uint16_t* flat = reinterpret_cast<uint16_t*>(ws + img_b + 2 * act_b);
   if (feats) {
     int rc = net_resize(c, feats, n_scans, images, st);
     if (rc) return rc;
   }
   // K4 conv towers
-  const float* cur = feats ? images : images_in;
+  const void* cur = feats ? images : images_in;
   int hw = n.R;
   for (size_t l = 0; l < n.convs.size(); ++l) {
     const NetConv& cv = n.convs[l];
     const bool last = l + 1 == n.convs.size();
-    ConvParams cp;
-    cp.in = cur;
-    cp.out = last ? static_cast<void*>(flat) : static_cast<void*>((l & 1) ? pong : ping);
-    for (int b = 0; b < 3; ++b) { cp.w[b] = cv.w[b]; cp.bias[b] = cv.bias[b]; }
-    cp.n_img = n_scans * 3; cp.H = hw; cp.W = hw; cp.Cin = cv.cin; cp.Cout = cv.cout;
-    cp.Ho = (hw + 1) / 2; cp.Wo = (hw + 1) / 2;
-    const int pad_total = (cp.Ho - 1) * 2 + 3 - hw;
-    cp.pad_t = cp.pad_l = pad_total > 0 ? pad_total / 2 : 0;   // TF 'same': extra padding goes after
-    cp.act = cv.act; cp.alpha = n.alpha; cp.out_bf16 = last ? 1 : 0;
-    const int smem = 9 * cv.cin * kConvCoutTile * 4;
-    RML_CUDA(c, cudaFuncSetAttribute(k4_conv3x3s2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int64_t pixels = n_scans * cp.Ho * cp.Wo;
-    int64_t gx = (pixels + 255) / 256;
-    if (gx > 8ll * c->num_sms) gx = 8ll * c->num_sms;
-    k4_conv3x3s2<<<dim3(static_cast<unsigned>(gx), cv.cout / kConvCoutTile, 3), 256, smem, st>>>(cp);
+    const int ho = (hw + 1) / 2;
+    const int pad_total = (ho - 1) * 2 + 3 - hw;
+    const int pad = pad_total > 0 ? pad_total / 2 : 0;       // TF 'same': extra padding goes after
+    void* dst = last ? static_cast<void*>(flat) : static_cast<void*>((l & 1) ? pong : ping);
+    if (l >= 1 && n.use_igemm) {
+      // tcgen05 implicit GEMM on the NHWC bf16 activation written by the previous layer
+      CUtensorMap map_x;
+      cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cv.cin), static_cast<cuuint64_t>(hw),
+                            static_cast<cuuint64_t>(hw), static_cast<cuuint64_t>(n_scans * 3)};
+      cuuint64_t gstr[3] = {static_cast<cuuint64_t>(cv.cin) * 2, static_cast<cuuint64_t>(hw) * cv.cin * 2,
+                            static_cast<cuuint64_t>(hw) * hw * cv.cin * 2};
+      int th = 128 / ho;
+      if (th > ho) th = ho;
+      cuuint32_t box[4] = {64u, static_cast<cuuint32_t>(2 * ho), static_cast<cuuint32_t>(2 * th), 1u};
+      cuuint32_t estr[4] = {1u, 2u, 2u, 1u};
+      CUresult r = c->encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(cur), gdim, gstr,
+                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(c, RML_E_CUDA, "cuTensorMapEncodeTiled(conv activation) failed: %d", (int)r);
+      ConvGemmParams gp;
+      gp.n_img = n_scans * 3; gp.Ho = ho; gp.Wo = ho; gp.Cin = cv.cin; gp.Cout = cv.cout; gp.TH = th;
+      gp.tiles_per_img = (ho + th - 1) / th; gp.pad_t = pad; gp.pad_l = pad;
+      gp.act = cv.act; gp.alpha = n.alpha; gp.bias = cv.bias3;
+      gp.out = reinterpret_cast<__nv_bfloat16*>(dst);
+      const int smem = cg_smem_bytes(cv.cout);
+      RML_CUDA(c, cudaFuncSetAttribute(k4_conv_igemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      const int64_t tiles = gp.n_img * gp.tiles_per_img;
+      const int grid = static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
+      k4_conv_igemm<<<grid, kCgThreads, smem, st>>>(map_x, cv.map_w, gp);
+    } else if (cv.cin == 1 && n.use_igemm && (cv.cout == 64 || cv.cout == 128)) {
+      Conv1Params c1;
+      c1.in = static_cast<const float*>(cur);
+      c1.out = reinterpret_cast<__nv_bfloat16*>(dst);
+      for (int b = 0; b < 3; ++b) { c1.w[b] = cv.w[b]; c1.bias[b] = cv.bias[b]; }
+      c1.n_img = n_scans * 3; c1.H = hw; c1.W = hw; c1.Cout = cv.cout; c1.Ho = ho; c1.Wo = ho;
+      c1.pad_t = c1.pad_l = pad; c1.act = cv.act; c1.alpha = n.alpha;
+      const int64_t tasks = c1.n_img * ((static_cast<int64_t>(ho) * ho + kConv1Run - 1) / kConv1Run);
+      int64_t blocks = (tasks + 7) / 8;
+      if (blocks > 16ll * c->num_sms) blocks = 16ll * c->num_sms;
+      if (cv.cout == 64) k4_conv1_cin1<2><<<static_cast<unsigned>(blocks), 256, 0, st>>>(c1);
+      else k4_conv1_cin1<4><<<static_cast<unsigned>(blocks), 256, 0, st>>>(c1);
+    } else {
+      ConvParams cp;
+      cp.in = static_cast<const float*>(cur);
+      cp.out = dst;
+      for (int b = 0; b < 3; ++b) { cp.w[b] = cv.w[b]; cp.bias[b] = cv.bias[b]; }
+      cp.n_img = n_scans * 3; cp.H = hw; cp.W = hw; cp.Cin = cv.cin; cp.Cout = cv.cout;
+      cp.Ho = ho; cp.Wo = ho; cp.pad_t = cp.pad_l = pad;
+      cp.act = cv.act; cp.alpha = n.alpha;
+      cp.out_bf16 = (last || n.use_igemm) ? 1 : 0;           // bf16 feeds the tensor-core layers
+      const int smem = 9 * cv.cin * kConvCoutTile * 4;
+      RML_CUDA(c, cudaFuncSetAttribute(k4_conv3x3s2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      const int64_t pixels = n_scans * ho * ho;
+      int64_t gx = (pixels + 255) / 256;
+      if (gx > 8ll * c->num_sms) gx = 8ll * c->num_sms;
+      k4_conv3x3s2<<<dim3(static_cast<unsigned>(gx), cv.cout / kConvCoutTile, 3), 256, smem, st>>>(cp);
+    }
     RML_CUDA(c, cudaGetLastError());
     ++c->launches;
-    cur = static_cast<const float*>(cp.out);
-    hw = cp.Ho;
+    cur = dst;
+    hw = ho;
   }
-  if (flat_out)
-    RML_CUDA(c, cudaMemcpyAsync(flat_out, flat, static_cast<size_t>(n_scans) * n.K * 2, cudaMemcpyDeviceToDevice, st));
-  // K5 dense stack on tcgen05
+  return RML_OK;
+}
+
+// K5 dense stack on tcgen05 over a whole dense group
+static int net_dense(rml_ctx* c, const uint16_t* flat, int64_t n_scans, float* proba, float* logits,
+                     int32_t* label, cudaStream_t st) {
+  Net& n = c->net;
   CUtensorMap map_act;
   int rc = encode_bf16_map(c, &map_act, flat, n_scans, n.K, kK5BlockM);
   if (rc) return rc;
@@ -1102,6 +1225,55 @@ static int net_forward_chunk(rml_ctx* c, const float* feats, const float* images
   return RML_OK;
 }
 
+// shared driver: conv towers chunk by chunk, dense stack once per dense group
+static int net_run(rml_ctx* c, const float* cubes, int mode, const int32_t* ijk, const float* feats,
+                   const float* images, int64_t B, void* workspace, size_t workspace_bytes, float* proba,
+                   float* logits, int32_t* label, uint16_t* tower_bf16, cudaStream_t st) {
+  NetPlan pl;
+  int rc = net_make_plan(c, B, workspace_bytes, &pl);
+  if (rc) return rc;
+  char* ws = static_cast<char*>(workspace);
+  uint16_t* flat = reinterpret_cast<uint16_t*>(ws + pl.flat_off);
+  float* feats_ws = reinterpret_cast<float*>(ws + pl.feats_off);
+  const int F = feature_len(c, RML_MASK_ALL);
+  const int C = c->net.C;
+  const int64_t K = c->net.K;
+  const size_t cube_elems = static_cast<size_t>(c->sx) * c->sy * c->sz;
+  const size_t img_elems = static_cast<size_t>(3) * c->net.R * c->net.R;
+  for (int64_t g0 = 0; g0 < B; g0 += pl.group) {
+    const int64_t gn = (B - g0) < pl.group ? (B - g0) : pl.group;
+    for (int64_t lo = 0; lo < gn; lo += pl.chunk) {
+      const int64_t n = (gn - lo) < pl.chunk ? (gn - lo) : pl.chunk;
+      const int64_t s0 = g0 + lo;
+      const float* f = nullptr;
+      const float* im = nullptr;
+      if (cubes) {
+        // K1 with the network's scaling (p - 127.5) / 127.5 (dnn.py:202-205)
+        const int saved = c->aff_enabled;
+        const float so = c->aff_offset, ss = c->aff_scale;
+        c->aff_enabled = 1; c->aff_offset = 127.5f; c->aff_scale = 127.5f;
+        rc = project_impl(c, cubes + s0 * cube_elems, n, mode, ijk ? ijk + s0 * 3 : nullptr, RML_MASK_ALL,
+                          RML_F32, feats_ws, nullptr, st);
+        c->aff_enabled = saved; c->aff_offset = so; c->aff_scale = ss;
+        if (rc) return rc;
+        f = feats_ws;
+      } else if (feats) {
+        f = feats + s0 * F;
+      } else {
+        im = images + s0 * img_elems;
+      }
+      rc = net_towers_chunk(c, f, im, n, ws, flat + lo * K, st);
+      if (rc) return rc;
+    }
+    if (tower_bf16)
+      RML_CUDA(c, cudaMemcpyAsync(tower_bf16 + g0 * K, flat, static_cast<size_t>(gn) * K * 2,
+                                  cudaMemcpyDeviceToDevice, st));
+    rc = net_dense(c, flat, gn, proba + g0 * C, logits ? logits + g0 * C : nullptr, label + g0, st);
+    if (rc) return rc;
+  }
+  return RML_OK;
+}
+
 int rml_net_forward(rml_ctx* c, const float* feats, int64_t B, void* workspace, size_t workspace_bytes,
                     float* proba, float* logits, int32_t* label, rml_stream stream) {
   if (!c) return RML_E_INVALID;
@@ -1109,18 +1281,8 @@ int rml_net_forward(rml_ctx* c, const float* feats, int64_t B, void* workspace, 
   if (!feats || !workspace || !proba || !label || B < 0) return fail(c, RML_E_INVALID, "rml_net_forward: null buffer or B<0");
   if (B == 0) return RML_OK;
   DeviceGuard g(c->device);
-  const size_t per = net_bytes_per_scan(c);
-  int64_t chunk = workspace_bytes > 4096 ? static_cast<int64_t>((workspace_bytes - 4096) / per) : 0;
-  if (chunk < 1) return fail(c, RML_E_INVALID, "rml_net_forward: workspace too small (%zu B per scan needed)", per);
-  const int F = feature_len(c, RML_MASK_ALL);
-  const int C = c->net.C;
-  for (int64_t lo = 0; lo < B; lo += chunk) {
-    const int64_t n = (B - lo) < chunk ? (B - lo) : chunk;
-    int rc = net_forward_chunk(c, feats + lo * F, nullptr, n, static_cast<char*>(workspace), proba + lo * C,
-                               logits ? logits + lo * C : nullptr, label + lo, static_cast<cudaStream_t>(stream));
-    if (rc) return rc;
-  }
-  return RML_OK;
+  return net_run(c, nullptr, 0, nullptr, feats, nullptr, B, workspace, workspace_bytes, proba, logits, label,
+                 nullptr, static_cast<cudaStream_t>(stream));
 }
 
 // dnn.py:240-254 alone: scaled projections -> [B][3][R][R] float32 (the Keras model's inputs)
@@ -1142,24 +1304,11 @@ int rml_net_forward_images(rml_ctx* c, const float* images, int64_t B, void* wor
   if (!images || !workspace || !proba || !label || B < 0) return fail(c, RML_E_INVALID, "rml_net_forward_images: null buffer or B<0");
   if (B == 0) return RML_OK;
   DeviceGuard g(c->device);
-  const size_t per = net_bytes_per_scan(c);
-  int64_t chunk = workspace_bytes > 4096 ? static_cast<int64_t>((workspace_bytes - 4096) / per) : 0;
-  if (chunk < 1) return fail(c, RML_E_INVALID, "rml_net_forward_images: workspace too small (%zu B per scan needed)", per);
-  const int C = c->net.C;
-  const size_t img_elems = static_cast<size_t>(3) * c->net.R * c->net.R;
-  for (int64_t lo = 0; lo < B; lo += chunk) {
-    const int64_t n = (B - lo) < chunk ? (B - lo) : chunk;
-    int rc = net_forward_chunk(c, nullptr, images + lo * img_elems, n, static_cast<char*>(workspace),
-                               proba + lo * C, logits ? logits + lo * C : nullptr, label + lo,
-                               static_cast<cudaStream_t>(stream),
-                               tower_bf16 ? tower_bf16 + lo * static_cast<int64_t>(c->net.K) : nullptr);
-    if (rc) return rc;
-  }
-  return RML_OK;
+  return net_run(c, nullptr, 0, nullptr, nullptr, images, B, workspace, workspace_bytes, proba, logits, label,
+                 tower_bf16, static_cast<cudaStream_t>(stream));
 }
 
-
-// cubes -> K1 (projection + (p-127.5)/127.5, dnn.py:202-205) -> K3 -> K4 -> K5, chunked
+// cubes -> K1 (projection + (p-127.5)/127.5, dnn.py:202-205) -> K3 -> K4 -> K5
 int rml_net_predict(rml_ctx* c, const float* cubes, int64_t B, int mode, const int32_t* ijk,
                     void* workspace, size_t workspace_bytes, float* proba, int32_t* label,
                     rml_stream stream) {
@@ -1168,28 +1317,8 @@ int rml_net_predict(rml_ctx* c, const float* cubes, int64_t B, int mode, const i
   if (!cubes || !workspace || !proba || !label || B < 0) return fail(c, RML_E_INVALID, "rml_net_predict: null buffer or B<0");
   if (B == 0) return RML_OK;
   DeviceGuard g(c->device);
-  const size_t per = net_bytes_per_scan(c);
-  int64_t chunk = workspace_bytes > 4096 ? static_cast<int64_t>((workspace_bytes - 4096) / per) : 0;
-  if (chunk < 1) return fail(c, RML_E_INVALID, "rml_net_predict: workspace too small (%zu B per scan needed)", per);
-  const int F = feature_len(c, RML_MASK_ALL);
-  const int C = c->net.C;
-  const size_t cube_elems = static_cast<size_t>(c->sx) * c->sy * c->sz;
-  const int saved = c->aff_enabled;
-  const float so = c->aff_offset, ss = c->aff_scale;
-  c->aff_enabled = 1; c->aff_offset = 127.5f; c->aff_scale = 127.5f;
-  int rc = RML_OK;
-  for (int64_t lo = 0; lo < B && rc == RML_OK; lo += chunk) {
-    const int64_t n = (B - lo) < chunk ? (B - lo) : chunk;
-    char* ws = static_cast<char*>(workspace);
-    // features of the chunk live behind the network buffers (fixed offset for every chunk)
-    float* feats = reinterpret_cast<float*>(ws + align256(net_core_bytes_per_scan(c) * static_cast<size_t>(chunk) + 1024));
-    rc = project_impl(c, cubes + lo * cube_elems, n, mode, ijk ? ijk + lo * 3 : nullptr, RML_MASK_ALL,
-                      RML_F32, feats, nullptr, static_cast<cudaStream_t>(stream));
-    if (rc == RML_OK)
-      rc = net_forward_chunk(c, feats, nullptr, n, ws, proba + lo * C, nullptr, label + lo, static_cast<cudaStream_t>(stream));
-  }
-  c->aff_enabled = saved; c->aff_offset = so; c->aff_scale = ss;
-  return rc;
+  return net_run(c, cubes, mode, ijk, nullptr, nullptr, B, workspace, workspace_bytes, proba, nullptr, label,
+                 nullptr, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

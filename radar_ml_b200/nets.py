@@ -166,6 +166,7 @@ class GpuNetClassifier:
                                          ACT[d2.act], _p(w3), _p(b3)))
         check(ctx, lib.rml_net_finish(ctx))
         self.K = K
+        self.uses_igemm = bool(lib.rml_net_uses_igemm(ctx))
 
     def _workspace(self):
         import torch

@@ -52,7 +52,8 @@ def test_forward_matches_oracle(eng, kind):
     n = 150 if kind == "dnn" else 40
     cubes, ijk, samples = _samples(n, 60)
     X = nets.preprocess(samples, spec.R)
-    P_bf, lg_bf = nets.forward(spec, X, bf16_points=True)
+    igemm = net.uses_igemm          # towers on tcgen05 (bf16 activations) or fp32 CUDA cores
+    P_bf, lg_bf = nets.forward_bf16_towers(spec, X) if igemm else nets.forward(spec, X, bf16_points=True)
     P_64, _ = nets.forward(spec, X)
     # Keras-style entry: model.predict([XZ, YZ, XY])
     got = net.predict([X[..., 0], X[..., 1], X[..., 2]]).astype(np.float64)
@@ -65,19 +66,21 @@ def test_forward_matches_oracle(eng, kind):
     proba, label, logits, tower = net.forward_images(images, want_logits=True, want_tower=True)
     hw = spec.R // (2 ** len(spec.branches[0]))
     t_gpu = nets.bf16_bits_to_float(tower.cpu().numpy()).reshape(n, 3, hw, hw, -1)
-    t_ref = nets.tower_output(spec, X)
-    # (1) conv towers: within one bf16 ulp of the float64 towers everywhere, equal to the
-    #     oracle's rounding almost everywhere
-    ulp = np.abs(t_ref) * 2.0 ** -7 + 1e-5      # + fp32 accumulation slack around zero (ReLU)
+    t_ref = nets.tower_output(spec, X, bf16_towers=igemm)
+    # (1) conv towers: within one bf16 ulp of the float64 towers (evaluated with the same
+    #     rounding points), equal to the oracle's rounding almost everywhere.  With bf16
+    #     activations inside the towers a boundary flip in layer 1 perturbs layer 2 slightly.
+    slack = 2e-3 * np.abs(t_ref).max() if igemm else 1e-5
+    ulp = np.abs(t_ref) * 2.0 ** -7 + slack
     assert (np.abs(t_gpu - t_ref) <= ulp).all()
-    assert (t_gpu != nets.bf16_round(t_ref).reshape(t_gpu.shape)).mean() < 1e-3
+    assert (t_gpu != nets.bf16_round(t_ref).reshape(t_gpu.shape)).mean() < (2e-2 if igemm else 1e-3)
     # (2) tcgen05 dense stack + head: 1e-5 against float64 on the very operands it consumed
     P_t, lg_t = nets.dense_from_tower(spec, t_gpu)
     assert np.abs(proba.cpu().numpy()[:, :P_t.shape[1]].astype(np.float64) - P_t).max() < TOL
     assert np.abs(got - P_t).max() < TOL
     assert np.abs(logits.cpu().numpy() - lg_t).max() < 2e-5
     # (3) end to end against the oracle's own rounding points
-    assert np.abs(got - P_bf).max() < 5e-5
+    assert np.abs(got - P_bf).max() < (5e-4 if igemm else 5e-5)
     if kind != "sgan_d":
         lab = label.cpu().numpy()
         srt = np.sort(P_bf, axis=1)
@@ -97,10 +100,10 @@ def test_predict_cubes_slice_mode_and_batch_invariance(eng):
     cubes, _, ijk = synth.make_cubes(70, seed=61)
     xz, yz, xy = synth.project_slice(cubes, ijk)
     X = nets.preprocess([(xz[i], yz[i], xy[i]) for i in range(70)], 80)
-    P_bf, _ = nets.forward(spec, X, bf16_points=True)
+    P_bf, _ = nets.forward_bf16_towers(spec, X) if net.uses_igemm else nets.forward(spec, X, bf16_points=True)
     d = torch.from_numpy(cubes).cuda()
     p, l = net.predict_cubes(d, mode="slice", ijk=torch.from_numpy(ijk).cuda())
-    assert np.abs(p.cpu().numpy() - P_bf).max() < 5e-5      # see test_forward_matches_oracle
+    assert np.abs(p.cpu().numpy() - P_bf).max() < (5e-4 if net.uses_igemm else 5e-5)   # see above
     # size-independent property: a scan's result does not depend on its batch or position
     perm = torch.randperm(70)
     p_perm, _ = net.predict_cubes(d[perm].contiguous(), mode="slice", ijk=torch.from_numpy(ijk)[perm].cuda())
