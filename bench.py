@@ -29,6 +29,10 @@ sys.path.insert(0, ROOT)
 
 CUBE_BYTES = 22 * 31 * 176 * 4            # 480 128 B, common.py:25-27
 ALGO_BYTES_PER_SCAN = CUBE_BYTES + 12 + 4  # + 3 fp32 probs + int32 label
+# dram__bytes_read.sum + dram__bytes_write.sum of k1_project_max<u8> per scan, from the ncu
+# --set full capture summarised in profiles/r1b_k1_project_max_u8_ncu.txt (7.86665 GB read +
+# 0.12745 GB written for 16 384 scans): 1.016 x the algorithmic bytes, i.e. no re-reads.
+K1_DRAM_TRAFFIC_PER_SCAN = (7.866650e9 + 127.451904e6) / 16384
 METRIC = "radar_scans_per_sec_proj_classify"
 
 
@@ -337,7 +341,9 @@ def run_ours(args):
                        "l2": "inputs (%.1f GB/GPU) larger than L2, no flush needed" % (B * CUBE_BYTES / 1e9),
                        "e2e_scans_per_step": Be},
             "roofline": {"bound": "hbm", "kernel": "k1_project_max<u8>", "achieved": k1_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": k1_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": k1_gbs / peak, "traffic": B * K1_DRAM_TRAFFIC_PER_SCAN,
+                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1b_k1_project_max_u8_ncu.txt)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_scan": CUBE_BYTES, "k1_ms": k1_ms,
                          "k2_exposed_ms": k2_ms, "fused_pipeline": bool(fused),
                          "path_frac": (value / world) * ALGO_BYTES_PER_SCAN / (peak * 1e9)},
