@@ -34,7 +34,8 @@ typedef enum rml_status {
   RML_E_CUDA = -2,         /* CUDA runtime or driver error, no usable device */
   RML_E_UNSUPPORTED = -3,  /* e.g. zoom != 1.0 projections requested of the fused kernel */
   RML_E_NOMODEL = -4,      /* scoring requested before rml_load_* */
-  RML_E_NONINTEGRAL = -5   /* u8 fast path saw a value that is not an integer in [0,255] */
+  RML_E_NONINTEGRAL = -5,  /* u8 fast path saw a value that is not an integer in [0,255] */
+  RML_E_RANGE = -6         /* digit path saw a feature outside [0, 256/feature_scale) */
 } rml_status;
 
 /* projection mode: predict.py:102-107 takes SLICES through the target voxel (i,j,k);
@@ -47,8 +48,11 @@ enum { RML_MASK_XZ = 1, RML_MASK_YZ = 2, RML_MASK_XY = 4, RML_MASK_ALL = 7 };
 /* feature dtypes produced by rml_project / consumed by rml_score */
 enum {
   RML_F32 = 0, /* float32 (n,F) exactly as common.process_samples returns (common.py:149) */
-  RML_U8 = 1   /* raw integer sensor value 0..255, K-padded rows, operand layout of the
+  RML_U8 = 1,  /* raw integer sensor value 0..255, K-padded rows, operand layout of the
                   tensor-core scorer; the /255 scale is folded into the scorer */
+  RML_F32_EXACT = 2 /* rml_score only: float32 features through the float64 CUDA-core scorer (any
+                  value range); plain RML_F32 uses the exact multi-digit tensor-core scorer, which
+                  needs every feature and support-vector component in [0, 256/feature_scale) */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------- */

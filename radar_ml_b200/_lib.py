@@ -16,10 +16,10 @@ LIB_PATH = os.path.join(_HERE, "libradarml.so")
 SRC = os.path.join(_HERE, "csrc", "radarml.cu")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "radarml.h")
 
-OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMODEL, E_NONINTEGRAL = 0, -1, -2, -3, -4, -5
+OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMODEL, E_NONINTEGRAL, E_RANGE = 0, -1, -2, -3, -4, -5, -6
 MODE_MAX, MODE_SLICE = 0, 1
 MASK_XZ, MASK_YZ, MASK_XY, MASK_ALL = 1, 2, 4, 7
-F32, U8 = 0, 1
+F32, U8, F32_EXACT = 0, 1, 2
 
 
 class RadarMLError(RuntimeError):
@@ -30,6 +30,10 @@ class RadarMLError(RuntimeError):
 
 class NonIntegralInput(RadarMLError):
     """The u8 tensor-core path saw a value that is not an integer in [0,255]."""
+
+
+class OutOfRangeInput(RadarMLError):
+    """The multi-digit tensor-core path saw a feature outside [0, 256/feature_scale)."""
 
 
 def nvcc_command(out=LIB_PATH):
@@ -127,4 +131,6 @@ def check(ctx, rc):
     msg = msg.decode() if msg else ""
     if rc == E_NONINTEGRAL:
         raise NonIntegralInput(rc, msg)
+    if rc == E_RANGE:
+        raise OutOfRangeInput(rc, msg)
     raise RadarMLError(rc, msg)

@@ -1,0 +1,259 @@
+// K2 general-precision scorer on the tensor cores: exact multi-digit integer distances.
+//
+// Non-integral features / support vectors (augmented training data train.py:84-185, zoomed
+// inputs common.py:143) cannot use the single u8 x u8 product of k2_rbf_i8, and a floating
+// GEMM form ||x||^2 + ||s||^2 - 2 x.s loses the distance to cancellation.  Instead every value
+// v = 255 x in [0, 256) is taken to 24-bit fixed point X = round(v * 2^16) = 65536 d2 + 256 d1 + d0
+// and the dot product is assembled from nine EXACT u8 x u8 -> s32 digit products:
+//     X . S = sum_p 256^p  sum_{a+b=p} (A_a . B_b),           p = 0..4
+// Each power p has its own s32 accumulator in TMEM (<= 3 x 6.5e8 < 2^31), the epilogue rebuilds
+// the 64-bit integer ||X - S||^2 = ||X||^2 + ||S||^2 - 2 X.S exactly and hands
+// exp(-gamma d^2) to the same fp64 tail as the integer kernel.  Quantisation is 2^-17 of one
+// sensor count (3e-8 of a [0,1] feature); everything after it is integer arithmetic, so the
+// result is deterministic and independent of the summation order.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "k2_score.cuh"
+#include "ptx.cuh"
+
+namespace rml {
+
+constexpr int kDgTileN = 96;          // support vectors per chunk: 5 accumulators x 96 = 480 TMEM columns
+constexpr int kDgStages = 2;
+constexpr int kDgABytes = kK2BlockM * kK2BlockKBytes;       // 16 384 per digit
+constexpr int kDgBBytes = kDgTileN * kK2BlockKBytes;        // 12 288 per digit
+constexpr int kDgStageBytes = 3 * (kDgABytes + kDgBBytes);  // 86 016
+
+struct K2DgParams {
+  int64_t B;
+  int n_sv, n_chunks, k_blocks, n_pad;
+  const long long* unorm;      // [B]     sum X^2
+  const long long* svnorm;     // [n_pad] sum S^2
+  const double* pairw;         // [NP][n_pad]
+  const double* rho;
+  const double* platt_a;
+  const double* platt_b;
+  double neg_gamma_fixed;      // -gamma / (feature_scale^2 * 2^32)
+  double min_proba;
+  float* proba;
+  float* decision;
+  int32_t* label;
+  uint8_t* known;
+};
+
+struct DgMaps {
+  CUtensorMap a[3];            // feature digit planes [B][kpad] u8
+  CUtensorMap b[3];            // support-vector digit planes [n_pad][kpad] u8
+};
+
+__host__ __device__ constexpr int k2dg_table_bytes(int n_pad, int n_pairs) {
+  return ((n_pad * (8 + 8 * n_pairs) + 127) / 128) * 128 + kK2BlockM * n_pairs * 8;
+}
+__host__ __device__ constexpr int k2dg_smem_bytes(int n_pad, int n_pairs) {
+  return kDgStages * kDgStageBytes + 1024 + 256 + k2dg_table_bytes(n_pad, n_pairs);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kK2Threads, 1)
+k2_rbf_digits(const __grid_constant__ DgMaps maps, const K2DgParams p) {
+  constexpr int NP = C * (C - 1) / 2;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDgStages * kDgStageBytes);
+  uint64_t* full = bars;                 // [2]
+  uint64_t* empty = bars + kDgStages;    // [2]
+  uint64_t* tfull = empty + kDgStages;   // [1]
+  uint64_t* tempty = tfull + 1;          // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+  unsigned char* tab = smem + kDgStages * kDgStageBytes + 256;
+  long long* s_norm = reinterpret_cast<long long*>(tab);                            // [n_pad]
+  double* s_w = reinterpret_cast<double*>(tab + p.n_pad * 8);                        // [NP][n_pad]
+  double* s_x = reinterpret_cast<double*>(tab + ((p.n_pad * (8 + 8 * NP) + 127) / 128) * 128);
+  for (int e = threadIdx.x; e < p.n_pad; e += blockDim.x) s_norm[e] = p.svnorm[e];
+  for (int e = threadIdx.x; e < p.n_pad * NP; e += blockDim.x) s_w[e] = p.pairw[e];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_tiles = (p.B + kK2BlockM - 1) / kK2BlockM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDgStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, kK2EpiWarps);
+    fence_barrier_init();
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      tma_prefetch_desc(&maps.a[d]);
+      tma_prefetch_desc(&maps.b[d]);
+    }
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_last();
+      uint32_t kit = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
+            const int s = kit % kDgStages;
+            mbar_wait(&empty[s], ((kit / kDgStages) & 1) ^ 1);
+            unsigned char* a_dst = smem + s * kDgStageBytes;
+            unsigned char* b_dst = a_dst + 3 * kDgABytes;
+            mbar_arrive_expect_tx(&full[s], kDgStageBytes);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              tma_load_2d(a_dst + d * kDgABytes, &maps.a[d], kb * kK2BlockKBytes,
+                          static_cast<int32_t>(tile * kK2BlockM), &full[s], pol);
+              tma_load_2d(b_dst + d * kDgBBytes, &maps.b[d], kb * kK2BlockKBytes, ch * kDgTileN, &full[s], pol);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(kCS32, kFmtU8, kFmtU8, kK2BlockM, kDgTileN);
+      uint32_t kit = 0, ait = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int ch = 0; ch < p.n_chunks; ++ch, ++ait) {
+          mbar_wait(tempty, (ait & 1) ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
+            const int s = kit % kDgStages;
+            mbar_wait(&full[s], (kit / kDgStages) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + s * kDgStageBytes);
+            const uint32_t b_addr = a_addr + 3 * kDgABytes;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+#pragma unroll
+              for (int b = 0; b < 3; ++b) {
+                const uint64_t da = umma_desc_k_sw128(a_addr + a * kDgABytes);
+                const uint64_t db = umma_desc_k_sw128(b_addr + b * kDgBBytes);
+                const uint32_t d_tmem = tmem_base + (a + b) * kDgTileN;
+                const bool first_pair = (a == 0) || (b == 2);   // first (a,b) of its power a+b
+#pragma unroll
+                for (int ks = 0; ks < kK2BlockKBytes / 32; ++ks)
+                  umma_i8(d_tmem, da + (ks * 32 >> 4), db + (ks * 32 >> 4), idesc,
+                          !(first_pair && kb == 0 && ks == 0));
+              }
+            }
+            umma_commit(&empty[s]);
+          }
+          umma_commit(tfull);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int m = q * 32 + lane;
+    uint32_t ait = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t b = tile * kK2BlockM + m;
+      const long long un = (b < p.B) ? p.unorm[b] : 0;
+      double dec[NP];
+#pragma unroll
+      for (int r = 0; r < NP; ++r) dec[r] = 0.0;
+      for (int ch = 0; ch < p.n_chunks; ++ch, ++ait) {
+        mbar_wait(tfull, ait & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        for (int c0 = half * 16; c0 < kDgTileN; c0 += 32) {
+          uint32_t v0[16], v1[16], v2[16], v3[16], v4[16];
+          tmem_ld_32x16(taddr + 0 * kDgTileN + c0, v0);
+          tmem_ld_32x16(taddr + 1 * kDgTileN + c0, v1);
+          tmem_ld_32x16(taddr + 2 * kDgTileN + c0, v2);
+          tmem_ld_32x16(taddr + 3 * kDgTileN + c0, v3);
+          tmem_ld_32x16(taddr + 4 * kDgTileN + c0, v4);
+          tmem_ld_wait();
+          const int n0 = ch * kDgTileN + c0;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int n = n0 + e;
+            const unsigned long long dot =
+                static_cast<unsigned long long>(v0[e]) + (static_cast<unsigned long long>(v1[e]) << 8) +
+                (static_cast<unsigned long long>(v2[e]) << 16) + (static_cast<unsigned long long>(v3[e]) << 24) +
+                (static_cast<unsigned long long>(v4[e]) << 32);
+            const long long d2 = un + s_norm[n] - 2ll * static_cast<long long>(dot);
+            const double kv = exp_neg_fast(static_cast<double>(d2) * p.neg_gamma_fixed);
+#pragma unroll
+            for (int r = 0; r < NP; ++r) dec[r] = fma(s_w[r * p.n_pad + n], kv, dec[r]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty);
+      }
+      if (half == 1) {
+#pragma unroll
+        for (int r = 0; r < NP; ++r) s_x[m * NP + r] = dec[r];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kK2EpiWarps * 32) : "memory");
+      if (half == 0 && b < p.B) {
+#pragma unroll
+        for (int r = 0; r < NP; ++r) dec[r] = dec[r] + s_x[m * NP + r] - p.rho[r];
+        double f[C];
+        ovr_transform<C>(dec, f);
+        platt_argmax_store<C>(f, p.platt_a, p.platt_b, p.min_proba, b, p.proba, p.decision, p.label, p.known);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kK2EpiWarps * 32) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// (n,F) float32 features scaled like common.process_samples(scale=True) -> three u8 digit planes
+// of X = round(x * scale * 2^16) and the exact 64-bit norms.  Values outside [0, 256/scale) cannot
+// be represented: they are clamped and counted in status[2] (RML_E_RANGE).
+struct DgQuantParams {
+  const float* feats;
+  uint8_t* planes;        // [3][B][stride]
+  long long* norms;       // [B]
+  unsigned int* status;
+  int64_t B;
+  int F, stride;
+  double scale;
+};
+__global__ void __launch_bounds__(256) k1_quantize_digits(const DgQuantParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = blockIdx.x * 8ll + warp;
+  if (b >= p.B) return;
+  const float* x = p.feats + b * p.F;
+  const int64_t plane = p.B * static_cast<int64_t>(p.stride);
+  uint8_t* o = p.planes + b * p.stride;
+  unsigned long long sumsq = 0;
+  uint32_t bad = 0;
+  for (int f = lane; f < p.stride; f += 32) {
+    uint32_t X = 0;
+    if (f < p.F) {
+      const double v = rint(static_cast<double>(x[f]) * p.scale * 65536.0);
+      bad |= !(v >= 0.0 && v < 16777216.0);
+      X = static_cast<uint32_t>(fmin(fmax(v, 0.0), 16777215.0));
+    }
+    o[f] = static_cast<uint8_t>(X & 255u);
+    o[plane + f] = static_cast<uint8_t>((X >> 8) & 255u);
+    o[2 * plane + f] = static_cast<uint8_t>(X >> 16);
+    sumsq += static_cast<unsigned long long>(X) * X;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sumsq += __shfl_xor_sync(0xffffffffu, sumsq, off);
+  if (lane == 0) p.norms[b] = static_cast<long long>(sumsq);
+  if (bad) atomicAdd(p.status + 2, 1u);
+}
+
+}  // namespace rml

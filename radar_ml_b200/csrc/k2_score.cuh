@@ -53,7 +53,6 @@ struct K2Params {
   float* decision;         // [B][C] or [B] (C == 2), nullable
   int32_t* label;          // [B]
   uint8_t* known;          // [B], nullable
-  int class_end[kMaxClasses];  // cumulative n_support
 };
 
 __host__ __device__ constexpr int k2_stage_bytes(int n_tile) {

@@ -182,21 +182,21 @@ struct Conv1Params {
   int act;
   float alpha;
 };
-constexpr int kConv1Run = 64;   // pixels per warp task
+constexpr int kConv1Run = 64;   // (host grid sizing) pixels per warp task, roughly
 
+// warp task = one output row of one image; 4 consecutive output pixels per step share their
+// 3 x 9 input taps (27 warp-uniform loads in flight instead of 9 dependent ones per pixel)
 template <int CPL>
 __global__ void __launch_bounds__(256) k4_conv1_cin1(const Conv1Params p) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  const int npix = p.Ho * p.Wo;
-  const int runs = (npix + kConv1Run - 1) / kConv1Run;
-  const int64_t tasks = p.n_img * runs;
+  const int64_t tasks = p.n_img * p.Ho;
   int cur_br = -1;
   float w[9][CPL], bs[CPL];
   for (int64_t task = warp_global; task < tasks; task += n_warps) {
-    const int64_t img = task / runs;
-    const int run = static_cast<int>(task - img * runs);
+    const int64_t img = task / p.Ho;
+    const int oy = static_cast<int>(task - img * p.Ho);
     const int br = static_cast<int>(img % 3);
     if (br != cur_br) {
       cur_br = br;
@@ -208,31 +208,40 @@ __global__ void __launch_bounds__(256) k4_conv1_cin1(const Conv1Params p) {
       for (int c = 0; c < CPL; ++c) bs[c] = p.bias[br][lane * CPL + c];
     }
     const float* in = p.in + img * static_cast<int64_t>(p.H) * p.W;
-    __nv_bfloat16* out = p.out + img * static_cast<int64_t>(npix) * p.Cout + lane * CPL;
-    const int p0 = run * kConv1Run;
-    const int p1 = p0 + kConv1Run < npix ? p0 + kConv1Run : npix;
-    for (int px = p0; px < p1; ++px) {
-      const int oy = px / p.Wo, ox = px - oy * p.Wo;
-      float acc[CPL];
-#pragma unroll
-      for (int c = 0; c < CPL; ++c) acc[c] = bs[c];
+    __nv_bfloat16* out = p.out + (img * p.Ho + oy) * static_cast<int64_t>(p.Wo) * p.Cout + lane * CPL;
+    const int iy0 = oy * 2 - p.pad_t;
+    for (int ox0 = 0; ox0 < p.Wo; ox0 += 4) {
+      const int ix0 = ox0 * 2 - p.pad_l;
+      float x[3][9];
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
-        const int iy = oy * 2 + kh - p.pad_t;
+        const int iy = iy0 + kh;
+        const bool rowok = iy >= 0 && iy < p.H;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int ix = ox * 2 + kw - p.pad_l;
-          float x = 0.f;
-          if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) x = __ldg(in + iy * p.W + ix);
-#pragma unroll
-          for (int c = 0; c < CPL; ++c) acc[c] = fmaf(x, w[kh * 3 + kw][c], acc[c]);
+        for (int cx = 0; cx < 9; ++cx) {
+          const int ix = ix0 + cx;
+          x[kh][cx] = (rowok && ix >= 0 && ix < p.W) ? __ldg(in + iy * p.W + ix) : 0.f;
         }
       }
-      __nv_bfloat16* o = out + static_cast<int64_t>(px) * p.Cout;
 #pragma unroll
-      for (int c = 0; c < CPL; c += 2)
-        *reinterpret_cast<__nv_bfloat162*>(o + c) =
-            __floats2bfloat162_rn(apply_act(acc[c], p.act, p.alpha), apply_act(acc[c + 1], p.act, p.alpha));
+      for (int px = 0; px < 4; ++px) {
+        if (ox0 + px < p.Wo) {
+          float acc[CPL];
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) acc[c] = bs[c];
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+              for (int c = 0; c < CPL; ++c) acc[c] = fmaf(x[kh][2 * px + kw], w[kh * 3 + kw][c], acc[c]);
+          __nv_bfloat16* o = out + static_cast<int64_t>(ox0 + px) * p.Cout;
+#pragma unroll
+          for (int c = 0; c < CPL; c += 2)
+            *reinterpret_cast<__nv_bfloat162*>(o + c) =
+                __floats2bfloat162_rn(apply_act(acc[c], p.act, p.alpha), apply_act(acc[c + 1], p.act, p.alpha));
+        }
+      }
     }
   }
 }

@@ -17,6 +17,7 @@
 
 #include "k1_project.cuh"
 #include "k2_score.cuh"
+#include "k2_digits.cuh"
 #include "k3_net.cuh"
 #include "k0_extras.cuh"
 
@@ -43,6 +44,13 @@ struct Model {
   double* platt_b = nullptr;
   int kpad = 0, n_tile = 0, n_chunks = 0;
   CUtensorMap map_sv;
+  // multi-digit exact path for non-integral values in [0, 256/scale)
+  bool digits_ok = false;
+  uint8_t* sv_digits = nullptr;   // [3][dg_pad][kpad]
+  long long* svnorm64 = nullptr;  // [dg_pad]
+  double* pairw_dg = nullptr;     // [NP][dg_pad]
+  int dg_pad = 0, dg_chunks = 0;
+  CUtensorMap map_sv_dg[3];
 };
 
 constexpr int kHostBufs = 3;
@@ -109,6 +117,10 @@ struct rml_ctx {
   int64_t fused_min_b = 8192;
   int fused_enabled = 1;     // RML_FUSED=0 disables
   int last_fused = 0;
+  // scratch of the multi-digit scorer (grow-only)
+  uint8_t* dg_planes = nullptr;
+  long long* dg_norms = nullptr;
+  int64_t dg_cap = 0;
   // zoom operators (common.py:143 ndimage.zoom as separable matrices), per projection
   double* zoom_ar[3] = {nullptr, nullptr, nullptr};
   double* zoom_ac[3] = {nullptr, nullptr, nullptr};
@@ -167,6 +179,9 @@ void free_model(Model& m) {
   cudaFree(m.sv_f64);
   cudaFree(m.coef);
   cudaFree(m.pairw);
+  cudaFree(m.sv_digits);
+  cudaFree(m.svnorm64);
+  cudaFree(m.pairw_dg);
   cudaFree(m.rho);
   cudaFree(m.platt_a);
   cudaFree(m.platt_b);
@@ -211,6 +226,17 @@ int launch_rbf_i8(rml_ctx* c, const CUtensorMap& map_feats, const K2Params& p, c
   return RML_OK;
 }
 template <int C>
+int launch_rbf_digits(rml_ctx* c, const DgMaps& maps, const K2DgParams& p, cudaStream_t st) {
+  const int smem = k2dg_smem_bytes(p.n_pad, C * (C - 1) / 2);
+  RML_CUDA(c, cudaFuncSetAttribute(k2_rbf_digits<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int64_t tiles = (p.B + kK2BlockM - 1) / kK2BlockM;
+  const int grid = static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
+  k2_rbf_digits<C><<<grid, kK2Threads, smem, st>>>(maps, p);
+  RML_CUDA(c, cudaGetLastError());
+  ++c->launches;
+  return RML_OK;
+}
+template <int C>
 int launch_rbf_general(rml_ctx* c, const K2GenParams& p, cudaStream_t st) {
   const int64_t grid = (p.B + 7) / 8;
   k2_rbf_general<C><<<static_cast<unsigned>(grid), 256, 0, st>>>(p);
@@ -237,9 +263,15 @@ int launch_linear(rml_ctx* c, const K2LinParams& p, cudaStream_t st) {
     default: return fail(c, RML_E_UNSUPPORTED, "n_classes=%d not in [2,6]", Cval); \
   }
 
+struct Affine {
+  float offset, scale;
+  int enabled;
+};
+
 int project_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int32_t* ijk,
                  uint32_t mask, int dtype, void* feats, int32_t* norms, cudaStream_t st,
-                 int grid_limit = 0, unsigned int* tile_done = nullptr) {
+                 int grid_limit = 0, unsigned int* tile_done = nullptr, const Affine* aff_in = nullptr) {
+  const Affine aff = aff_in ? *aff_in : Affine{c->aff_offset, c->aff_scale, c->aff_enabled};
   if (B < 0 || !cubes || !feats) return fail(c, RML_E_INVALID, "rml_project: null buffer or B<0");
   if ((mask & RML_MASK_ALL) == 0 || (mask & ~RML_MASK_ALL))
     return fail(c, RML_E_INVALID, "rml_project: mask %u selects no projection", mask);
@@ -256,7 +288,7 @@ int project_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
     K1Params p;
     p.cubes = cubes; p.feats = feats; p.norms = norms; p.status = c->status; p.B = B;
     p.stride = stride; p.F = F; p.mask = mask;
-    p.offset = c->aff_offset; p.scale = c->aff_scale; p.affine = c->aff_enabled;
+    p.offset = aff.offset; p.scale = aff.scale; p.affine = aff.enabled;
     p.tile_done = dtype == RML_U8 ? tile_done : nullptr;
     const int sms = grid_limit > 0 ? grid_limit : c->num_sms;
     const int grid = static_cast<int>(B < sms ? B : sms);
@@ -273,7 +305,7 @@ int project_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
     K1GenParams p;
     p.cubes = cubes; p.ijk = ijk; p.feats = feats; p.norms = norms; p.status = c->status; p.B = B;
     p.sx = c->sx; p.sy = c->sy; p.sz = c->sz; p.stride = stride; p.F = F; p.mask = mask;
-    p.offset = c->aff_offset; p.scale = c->aff_scale; p.affine = c->aff_enabled; p.mode = mode;
+    p.offset = aff.offset; p.scale = aff.scale; p.affine = aff.enabled; p.mode = mode;
     const int64_t want = B < 8ll * c->num_sms ? B : 8ll * c->num_sms;
     const int grid = static_cast<int>(want);
     if (dtype == RML_U8) k1_project_generic<uint8_t><<<grid, 256, 0, st>>>(p);
@@ -290,10 +322,11 @@ int score_impl(rml_ctx* c, const void* feats, int dtype, const int32_t* norms, i
   Model& m = c->model;
   if (m.kind == 0) return fail(c, RML_E_NOMODEL, "rml_score: no model loaded");
   if (!feats || !proba || !label || B < 0) return fail(c, RML_E_INVALID, "rml_score: null buffer or B<0");
+  if (dtype != RML_F32 && dtype != RML_U8 && dtype != RML_F32_EXACT) return fail(c, RML_E_INVALID, "rml_score: bad dtype %d", dtype);
   if (B == 0) return RML_OK;
   if (m.kind == 2) {
     K2LinParams p;
-    p.B = B; p.F = m.F; p.dtype = dtype;
+    p.B = B; p.F = m.F; p.dtype = dtype == RML_U8 ? 1 : 0;
     p.stride = dtype == RML_U8 ? round_up(m.F, 128) : m.F;
     p.feats = feats; p.coef = m.coef; p.intercept = m.rho; p.platt_a = m.platt_a; p.platt_b = m.platt_b;
     p.inv_scale = 1.0 / m.feature_scale; p.feature_scale = m.feature_scale; p.min_proba = min_proba;
@@ -318,9 +351,39 @@ int score_impl(rml_ctx* c, const void* feats, int dtype, const int32_t* norms, i
     p.platt_a = m.platt_a; p.platt_b = m.platt_b;
     p.neg_gamma_s2 = -m.gamma / (m.feature_scale * m.feature_scale);
     p.min_proba = min_proba; p.proba = proba; p.decision = decision; p.label = label; p.known = known;
-    for (int i = 0; i < kMaxClasses; ++i) p.class_end[i] = m.class_end[i];
     p.tile_ready = tile_ready;
     DISPATCH_C(m.C, launch_rbf_i8<CC>(c, map_feats, p, st, grid_limit));
+  }
+  if (dtype == RML_F32 && m.digits_ok) {
+    // tensor-core exact path: float32 features -> 24-bit fixed point digit planes -> 9 u8 GEMMs
+    if (reinterpret_cast<uintptr_t>(feats) & 3) return fail(c, RML_E_INVALID, "feats must be 4-byte aligned");
+    if (c->dg_cap < B) {
+      cudaFree(c->dg_planes); cudaFree(c->dg_norms);
+      c->dg_planes = nullptr; c->dg_norms = nullptr; c->dg_cap = 0;
+      RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->dg_planes), static_cast<size_t>(3) * B * m.kpad));
+      RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->dg_norms), static_cast<size_t>(B) * 8));
+      c->dg_cap = B;
+    }
+    DgQuantParams qp;
+    qp.feats = static_cast<const float*>(feats); qp.planes = c->dg_planes; qp.norms = c->dg_norms;
+    qp.status = c->status; qp.B = B; qp.F = m.F; qp.stride = m.kpad; qp.scale = m.feature_scale;
+    k1_quantize_digits<<<static_cast<unsigned>((B + 7) / 8), 256, 0, st>>>(qp);
+    RML_CUDA(c, cudaGetLastError());
+    ++c->launches;
+    DgMaps maps;
+    const size_t plane = static_cast<size_t>(B) * m.kpad;
+    for (int d = 0; d < 3; ++d) {
+      int rc = encode_u8_map(c, &maps.a[d], c->dg_planes + d * plane, B, m.F, m.kpad, kK2BlockM);
+      if (rc) return rc;
+      maps.b[d] = m.map_sv_dg[d];
+    }
+    K2DgParams dp;
+    dp.B = B; dp.n_sv = m.n_sv; dp.n_chunks = m.dg_chunks; dp.k_blocks = m.kpad / 128; dp.n_pad = m.dg_pad;
+    dp.unorm = c->dg_norms; dp.svnorm = m.svnorm64; dp.pairw = m.pairw_dg; dp.rho = m.rho;
+    dp.platt_a = m.platt_a; dp.platt_b = m.platt_b;
+    dp.neg_gamma_fixed = -m.gamma / (m.feature_scale * m.feature_scale * 4294967296.0);
+    dp.min_proba = min_proba; dp.proba = proba; dp.decision = decision; dp.label = label; dp.known = known;
+    DISPATCH_C(m.C, launch_rbf_digits<CC>(c, maps, dp, st));
   }
   K2GenParams p;
   p.B = B; p.F = m.F; p.n_sv = m.n_sv; p.feats = static_cast<const float*>(feats); p.sv = m.sv_f64;
@@ -349,10 +412,8 @@ int predict_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
   const size_t stride = feature_stride(c, mask, dtype);
   const size_t feat_bytes = align256(static_cast<size_t>(B) * stride * (dtype == RML_U8 ? 1 : 4));
   int32_t* norms = reinterpret_cast<int32_t*>(static_cast<char*>(work) + feat_bytes);
-  const int saved = c->aff_enabled;
-  const float so = c->aff_offset, ss = c->aff_scale;
   // the scorer expects features scaled like common.process_samples(scale=True)
-  c->aff_enabled = 1; c->aff_offset = 0.f; c->aff_scale = static_cast<float>(c->model.feature_scale);
+  const Affine aff{0.f, static_cast<float>(c->model.feature_scale), 1};
   const bool fused = c->fused_enabled && c->model.kind == 1 && dtype == RML_U8 && mode == RML_MODE_MAX &&
                      c->sx == kSX && c->sy == kSY && c->sz == kSZ && B >= c->fused_min_b &&
                      c->k2_sms > 0 && c->k2_sms < c->num_sms;
@@ -377,9 +438,8 @@ int predict_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
     RML_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
     if (c->ev_k1a) RML_CUDA(c, cudaEventRecord(c->ev_k1a, st));
     int rc = project_impl(c, cubes, B, mode, ijk, mask, dtype, work, norms, st,
-                          c->num_sms - c->k2_sms, c->tile_done);
+                          c->num_sms - c->k2_sms, c->tile_done, &aff);
     if (c->ev_k1b) RML_CUDA(c, cudaEventRecord(c->ev_k1b, st));
-    c->aff_enabled = saved; c->aff_offset = so; c->aff_scale = ss;
     if (rc) return rc;
     rc = score_impl(c, work, dtype, norms, B, min_proba, proba, nullptr, label, known, c->aux_stream,
                     c->k2_sms, c->tile_done);
@@ -390,9 +450,8 @@ int predict_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
     return RML_OK;
   }
   if (c->ev_k1a) RML_CUDA(c, cudaEventRecord(c->ev_k1a, st));
-  int rc = project_impl(c, cubes, B, mode, ijk, mask, dtype, work, norms, st);
+  int rc = project_impl(c, cubes, B, mode, ijk, mask, dtype, work, norms, st, 0, nullptr, &aff);
   if (c->ev_k1b) RML_CUDA(c, cudaEventRecord(c->ev_k1b, st));
-  c->aff_enabled = saved; c->aff_offset = so; c->aff_scale = ss;
   if (rc) return rc;
   rc = score_impl(c, work, dtype, norms, B, min_proba, proba, nullptr, label, known, st);
   if (c->ev_k2b && rc == RML_OK) RML_CUDA(c, cudaEventRecord(c->ev_k2b, st));
@@ -480,6 +539,8 @@ int rml_destroy(rml_ctx* c) {
   for (cudaEvent_t e : {c->ev_fork, c->ev_join, c->ev_k1a, c->ev_k1b, c->ev_k2b})
     if (e) cudaEventDestroy(e);
   cudaFree(c->tile_done);
+  cudaFree(c->dg_planes);
+  cudaFree(c->dg_norms);
   free_net(c->net);
   for (int q = 0; q < 3; ++q) { cudaFree(c->zoom_ar[q]); cudaFree(c->zoom_ac[q]); }
   cudaFree(c->status);
@@ -572,6 +633,50 @@ int rml_load_svc_rbf(rml_ctx* c, int C, int F, int n_sv, const int32_t* n_suppor
     if ((rc = upload(c, &m.sv_u8, u8.data(), u8.size()))) return rc;
     if ((rc = upload(c, &m.svnorm, norm.data(), norm.size()))) return rc;
     if ((rc = encode_u8_map(c, &m.map_sv, m.sv_u8, n_sv, F, m.kpad, m.n_tile))) return rc;
+  }
+  // digit planes: every component in [0, 256/scale) and room for 3 products per s32 accumulator
+  {
+    bool ok = static_cast<double>(F) * 65025.0 * 3.0 < 2147483647.0;
+    m.dg_chunks = (n_sv + kDgTileN - 1) / kDgTileN;
+    m.dg_pad = m.dg_chunks * kDgTileN;
+    const int NP = C * (C - 1) / 2;
+    if (k2dg_smem_bytes(m.dg_pad, NP) > 232448) ok = false;
+    std::vector<uint8_t> dg;
+    std::vector<long long> n64(m.dg_pad, 0);
+    if (ok) dg.assign(static_cast<size_t>(3) * m.dg_pad * m.kpad, 0);
+    const size_t plane = static_cast<size_t>(m.dg_pad) * m.kpad;
+    for (int n = 0; n < n_sv && ok; ++n) {
+      unsigned long long s2 = 0;
+      for (int f = 0; f < F; ++f) {
+        const double v = std::nearbyint(sv[static_cast<size_t>(n) * F + f] * feature_scale * 65536.0);
+        if (!(v >= 0.0 && v < 16777216.0)) { ok = false; break; }
+        const uint32_t X = static_cast<uint32_t>(v);
+        const size_t o = static_cast<size_t>(n) * m.kpad + f;
+        dg[o] = static_cast<uint8_t>(X & 255u);
+        dg[plane + o] = static_cast<uint8_t>((X >> 8) & 255u);
+        dg[2 * plane + o] = static_cast<uint8_t>(X >> 16);
+        s2 += static_cast<unsigned long long>(X) * X;
+      }
+      n64[n] = static_cast<long long>(s2);
+    }
+    m.digits_ok = ok;
+    if (ok) {
+      std::vector<double> pw(static_cast<size_t>(NP) * m.dg_pad, 0.0);
+      for (int n = 0, cls = 0; n < n_sv; ++n) {
+        while (n >= m.class_end[cls]) ++cls;
+        int pidx = 0;
+        for (int i = 0; i < C; ++i)
+          for (int j = i + 1; j < C; ++j, ++pidx) {
+            if (cls == i) pw[static_cast<size_t>(pidx) * m.dg_pad + n] = dual_coef[static_cast<size_t>(j - 1) * n_sv + n];
+            else if (cls == j) pw[static_cast<size_t>(pidx) * m.dg_pad + n] = dual_coef[static_cast<size_t>(i) * n_sv + n];
+          }
+      }
+      if ((rc = upload(c, &m.sv_digits, dg.data(), dg.size()))) return rc;
+      if ((rc = upload(c, &m.svnorm64, n64.data(), n64.size()))) return rc;
+      if ((rc = upload(c, &m.pairw_dg, pw.data(), pw.size()))) return rc;
+      for (int d = 0; d < 3; ++d)
+        if ((rc = encode_u8_map(c, &m.map_sv_dg[d], m.sv_digits + d * plane, n_sv, F, m.kpad, kDgTileN))) return rc;
+    }
   }
   if ((rc = upload(c, &m.sv_f64, sv, static_cast<size_t>(n_sv) * F))) return rc;
   if ((rc = upload(c, &m.coef, dual_coef, static_cast<size_t>(C - 1) * n_sv))) return rc;
@@ -758,6 +863,7 @@ int rml_check_status(rml_ctx* c, rml_stream stream) {
   RML_CUDA(c, cudaMemsetAsync(c->status, 0, 16, st));
   RML_CUDA(c, cudaStreamSynchronize(st));
   if (h[1]) return fail(c, RML_E_INVALID, "SLICE mode: %u scans had a target index outside the cube (numpy IndexError)", h[1]);
+  if (h[2]) return fail(c, RML_E_RANGE, "digit path: %u scans had features outside [0, 256/scale); score them as RML_F32_EXACT", h[2]);
   if (h[0]) return fail(c, RML_E_NONINTEGRAL, "u8 path: %u warps saw values that are not integers in [0,255]; use RML_F32", h[0]);
   return RML_OK;
 }
@@ -1174,7 +1280,7 @@ static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_
       for (int b = 0; b < 3; ++b) { c1.w[b] = cv.w[b]; c1.bias[b] = cv.bias[b]; }
       c1.n_img = n_scans * 3; c1.H = hw; c1.W = hw; c1.Cout = cv.cout; c1.Ho = ho; c1.Wo = ho;
       c1.pad_t = c1.pad_l = pad; c1.act = cv.act; c1.alpha = n.alpha;
-      const int64_t tasks = c1.n_img * ((static_cast<int64_t>(ho) * ho + kConv1Run - 1) / kConv1Run);
+      const int64_t tasks = c1.n_img * ho;     // one warp task per output row
       int64_t blocks = (tasks + 7) / 8;
       if (blocks > 16ll * c->num_sms) blocks = 16ll * c->num_sms;
       if (cv.cout == 64) k4_conv1_cin1<2><<<static_cast<unsigned>(blocks), 256, 0, st>>>(c1);
@@ -1249,12 +1355,9 @@ static int net_run(rml_ctx* c, const float* cubes, int mode, const int32_t* ijk,
       const float* im = nullptr;
       if (cubes) {
         // K1 with the network's scaling (p - 127.5) / 127.5 (dnn.py:202-205)
-        const int saved = c->aff_enabled;
-        const float so = c->aff_offset, ss = c->aff_scale;
-        c->aff_enabled = 1; c->aff_offset = 127.5f; c->aff_scale = 127.5f;
+        const Affine aff{127.5f, 127.5f, 1};
         rc = project_impl(c, cubes + s0 * cube_elems, n, mode, ijk ? ijk + s0 * 3 : nullptr, RML_MASK_ALL,
-                          RML_F32, feats_ws, nullptr, st);
-        c->aff_enabled = saved; c->aff_offset = so; c->aff_scale = ss;
+                          RML_F32, feats_ws, nullptr, st, 0, nullptr, &aff);
         if (rc) return rc;
         f = feats_ws;
       } else if (feats) {

@@ -12,7 +12,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import F32, MASK_ALL, MODE_MAX, MODE_SLICE, U8, NonIntegralInput, RadarMLError, check
+from ._lib import (F32, F32_EXACT, MASK_ALL, MODE_MAX, MODE_SLICE, U8, NonIntegralInput,
+                   OutOfRangeInput, RadarMLError, check)
 
 SX, SY, SZ = 22, 31, 176  # common.py:25-27 -> predict.py:74-76
 
@@ -205,13 +206,17 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ K2
-    def score(self, feats, norms=None, min_proba=0.7, want_decision=False):
-        """features -> (proba [B,C] f32, label [B] i32, known [B] bool[, decision])."""
+    def score(self, feats, norms=None, min_proba=0.7, want_decision=False, exact=False):
+        """features -> (proba [B,C] f32, label [B] i32, known [B] bool[, decision]).
+
+        uint8 rows (+ norms) take the integer tensor-core scorer; float32 rows take the exact
+        multi-digit tensor-core scorer (values in [0, 256/scale), checked by ``check_status``) or,
+        with ``exact=True`` / when the model does not qualify, the float64 CUDA-core scorer."""
         if self.params is None:
             raise RadarMLError(_lib.E_NOMODEL, "no model loaded")
         B = feats.shape[0]
         Cn = self.params.n_classes
-        dtype = U8 if feats.dtype == torch.uint8 else F32
+        dtype = U8 if feats.dtype == torch.uint8 else (F32_EXACT if exact else F32)
         proba = torch.empty((B, Cn), device=self.device, dtype=torch.float32)
         label = torch.empty((B,), device=self.device, dtype=torch.int32)
         known = torch.empty((B,), device=self.device, dtype=torch.uint8)
@@ -252,6 +257,10 @@ class Engine:
             proba, label, known = self.score(q, norms, min_proba)
         else:
             proba, label, known = self.score(x, None, min_proba)
+            try:
+                self.check_status()
+            except OutOfRangeInput:      # negative / oversize values: float64 CUDA-core scorer
+                proba, label, known = self.score(x, None, min_proba, exact=True)
         torch.cuda.synchronize(self.device)
         return proba.cpu().numpy(), label.cpu().numpy(), known.cpu().numpy()
 

@@ -124,7 +124,12 @@ def _classify_zoomed(cubes, ijk, gm, le, min_proba, proj_mask, proj_zoom, dims):
     finally:
         eng.set_affine(0.0, common.RADAR_MAX, True)
         eng.set_arena(*saved)
+    from ._lib import OutOfRangeInput
     proba, label, known = eng.score(feats, None, min_proba)
+    try:
+        eng.check_status()
+    except OutOfRangeInput:   # spline overshoot below 0 / above 255: float64 CUDA-core scorer
+        proba, label, known = eng.score(feats, None, min_proba, exact=True)
     P, lab, known = proba.cpu().numpy(), label.cpu().numpy(), known.cpu().numpy().astype(bool)
     best = P[np.arange(P.shape[0]), lab]
     names = np.where(known, np.asarray(le.classes_)[lab], 'Unknown')

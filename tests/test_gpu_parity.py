@@ -486,3 +486,76 @@ def test_dataset_roundtrip_and_evaluate_model(eng, small_problem, tmp_path):
         assert abs(row["precision"] - ref[row["class"]]["precision"]) < 1e-12
         assert abs(row["recall"] - ref[row["class"]]["recall"]) < 1e-12
         assert row["support"] == ref[row["class"]]["support"]
+
+
+def test_tiny_model_and_four_classes(eng):
+    """Edge shapes of the tensor-core scorer: a handful of support vectors (one 16-column MMA),
+    and C = 4 (six OvO pairs through the per-pair weight table)."""
+    import warnings
+    import torch
+    from oracle import restate, synth
+    from radar_ml_b200.model import from_sklearn
+    for n_classes, n_fit in ((3, 9), (4, 160)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            cubes, y, _ = synth.make_cubes(n_fit + 60 + 33, seed=70 + n_classes, n_classes=n_classes)
+            y[:n_classes] = np.arange(n_classes)               # every class present in the tiny fit
+            X = synth.features(*synth.project_max(cubes))
+            cal = synth.build_svc(X[:n_fit], y[:n_fit], X[n_fit:n_fit + 60], y[n_fit:n_fit + 60])
+        p = restate.export_params(cal)
+        eng.load_model(from_sklearn(cal))
+        assert eng.model_is_integral
+        test = cubes[n_fit + 60:]
+        _, lab_o, _, known_o, P_o = restate.scan_path(test, p, mode="max")
+        proba, label, known = eng.predict(torch.from_numpy(test).cuda(), mode="max")
+        eng.check_status()
+        assert proba.shape == (33, n_classes)
+        assert np.abs(proba.cpu().numpy().astype(np.float64) - P_o).max() < PROBA_TOL
+        srt = np.sort(P_o, axis=1)
+        clear = (srt[:, -1] - srt[:, -2]) > 1e-6            # exact ties are arg-max-order dependent
+        assert np.array_equal(label.cpu().numpy()[clear], lab_o[clear])
+        assert np.array_equal(known.cpu().numpy().astype(bool)[clear], known_o[clear])
+
+
+def test_multidigit_scorer_on_nonintegral_data(eng):
+    """Augmented-style model (non-integer support vectors, train.py:84-185) and non-integer
+    inputs: the exact 24-bit fixed-point tensor-core scorer vs the float64 oracle, and vs the
+    float64 CUDA-core scorer; out-of-range values are reported, never scored silently."""
+    import warnings
+    import torch
+    from oracle import restate, synth
+    from radar_ml_b200._lib import OutOfRangeInput
+    from radar_ml_b200.model import from_sklearn
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cubes, y, _ = synth.make_cubes(330, seed=404, integer=False)
+        cubes = np.clip(cubes, 0.0, 255.0).astype(np.float32)         # real-valued, in range
+        X = synth.features(*synth.project_max(cubes))
+        cal = synth.build_svc(X[:200], y[:200], X[200:260], y[200:260])
+    p = restate.export_params(cal)
+    eng.load_model(from_sklearn(cal))
+    assert not eng.model_is_integral
+    Xt = X[260:]
+    lab_o, _, known_o, P_o = restate.classify_batch(Xt, p, 0.7)
+    xt = torch.from_numpy(Xt).cuda()
+    proba, label, known = eng.score(xt, None, 0.7)                    # multi-digit tensor-core path
+    eng.check_status()
+    proba_x, label_x, known_x = eng.score(xt, None, 0.7, exact=True)  # float64 CUDA cores
+    for pr, lb, kn in ((proba, label, known), (proba_x, label_x, known_x)):
+        assert np.abs(pr.cpu().numpy().astype(np.float64) - P_o).max() < PROBA_TOL
+        assert np.array_equal(lb.cpu().numpy(), lab_o)
+        assert np.array_equal(kn.cpu().numpy(), known_o)
+    assert np.abs(proba.cpu().numpy() - proba_x.cpu().numpy()).max() < 1e-6
+    # sklearn-style entry point on host features
+    from radar_ml_b200.model import GpuCalibratedClassifier
+    gm = GpuCalibratedClassifier(from_sklearn(cal), engine=eng)
+    assert np.abs(gm.predict_proba(Xt) - P_o).max() < PROBA_TOL
+    # values the fixed-point digits cannot hold: flagged, then the exact scorer takes over
+    bad = Xt.copy()
+    bad[3, 17] = -0.02
+    bad[5, 100] = 1.5
+    eng.score(torch.from_numpy(bad).cuda(), None, 0.7)
+    with pytest.raises(OutOfRangeInput):
+        eng.check_status()
+    P_bad = restate.predict_proba(bad, p)
+    assert np.abs(gm.predict_proba(bad) - P_bad).max() < PROBA_TOL
