@@ -139,9 +139,10 @@ def build_model(seed=1234):
     """SVC-RBF C=10 gamma=0.01 (train_svc.log:24-31) on the reference's split sizes
     (909 train / 114 val, train_svc.log:11-13), synthetic MAX-projection features."""
     from oracle import synth
+    n_train = int(os.environ.get("RML_BENCH_TRAIN", "909"))     # test hook: a smaller fit
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        return synth.standard_model(seed=seed, mode="max")
+        return synth.standard_model(n_train=n_train, n_val=max(30, n_train // 8), seed=seed, mode="max")
 
 
 # ------------------------------------------------------------------------------ reference arm
@@ -152,7 +153,7 @@ def run_reference(args):
     from oracle import cpu_baseline, synth
     cores = cpu_baseline.host_cores()
     per_gpu = args.scans_per_gpu or (65536 if args.gpus == 1 else 131072)
-    sample = 4096
+    sample = int(os.environ.get("RML_BENCH_SAMPLE", "4096"))   # bounded CPU sample per step
     log("[reference] fitting model, generating %d sample scans on the host" % sample)
     cal = build_model()
     cubes, _, _ = synth.make_cubes(sample, seed=4321)

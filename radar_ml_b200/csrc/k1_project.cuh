@@ -218,8 +218,6 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
   __syncthreads();
 
   const int off_xz = 0;
-  const int off_yz = (p.mask & 1u) ? kFxz : 0;
-  const int off_xy = off_yz + ((p.mask & 2u) ? kFyz : 0);
   const float NEG = -FLT_MAX;
 
   uint32_t it = 0;  // running slab counter (identical in every role)

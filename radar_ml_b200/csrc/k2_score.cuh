@@ -141,11 +141,11 @@ __device__ __forceinline__ void platt_argmax_store(const double (&f)[C], const d
 // OvO decision values (libsvm pair order) -> what SVC.decision_function returns.
 template <int C>
 __device__ __forceinline__ void ovr_transform(const double (&dec)[C * (C - 1) / 2], double (&f)[C]) {
-  if (C == 2) {
+  if constexpr (C == 2) {
     f[0] = -dec[0];  // SK/svm/_base.py binary sign flip
     f[1] = 0.0;
     return;
-  }
+  } else {
   double votes[C], soc[C];
 #pragma unroll
   for (int k = 0; k < C; ++k) votes[k] = soc[k] = 0.0;
@@ -162,6 +162,7 @@ __device__ __forceinline__ void ovr_transform(const double (&dec)[C * (C - 1) / 
     }
 #pragma unroll
   for (int k = 0; k < C; ++k) f[k] = votes[k] + soc[k] / (3.0 * (fabs(soc[k]) + 1.0));
+  }
 }
 
 template <int C>

@@ -433,6 +433,8 @@ int predict_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
       RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->tile_done), tiles * sizeof(unsigned int)));
       c->tile_done_cap = tiles;
     }
+    // a previous fused call (possibly on another stream) may still be reading the counters
+    RML_CUDA(c, cudaStreamWaitEvent(st, c->ev_join, 0));
     RML_CUDA(c, cudaMemsetAsync(c->tile_done, 0, tiles * sizeof(unsigned int), st));
     RML_CUDA(c, cudaEventRecord(c->ev_fork, st));
     RML_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
