@@ -246,6 +246,103 @@ __global__ void __launch_bounds__(256) k4_conv1_cin1(const Conv1Params p) {
   }
 }
 
+// ------------------------------------------------------------------------------ K3+K4 fused
+// PIL resize (k3_resize_pil arithmetic, bit-exact) + the first tower layer (Cin = 1) in one CTA
+// per (scan, branch): the projection, the horizontal-pass result and the resized R x R image
+// never leave shared memory; only the bf16 NHWC activation of layer 1 is written.
+struct ResizeConv1Params {
+  ResizeParams rz;        // rz.images unused
+  __nv_bfloat16* out;     // [n_img][Ho][Wo][Cout]
+  const float* w[3];      // per branch [9][Cout]
+  const float* bias[3];
+  int Cout, Ho, Wo, pad_t, pad_l;
+  int act;
+  float alpha;
+};
+
+template <int CPL>
+__global__ void __launch_bounds__(256) k34_resize_conv1(const ResizeConv1Params p) {
+  extern __shared__ float rc_smem[];
+  const int br = blockIdx.y;
+  const int H = p.rz.ph[br], W = p.rz.pw[br], R = p.rz.R;
+  float* src = rc_smem;               // [H][W]
+  float* tmp = src + H * W;           // [H][R]
+  float* img = tmp + H * R;           // [R][R]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float w[9][CPL], bs[CPL];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) w[t][c] = p.w[br][t * p.Cout + lane * CPL + c];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) bs[c] = p.bias[br][lane * CPL + c];
+  const double* kh = p.rz.kh[br];
+  const double* kv = p.rz.kv[br];
+  const int2* bh = p.rz.bh[br];
+  const int2* bv = p.rz.bv[br];
+  const int ksh = p.rz.ksh[br], ksv = p.rz.ksv[br];
+  for (int64_t b = blockIdx.x; b < p.rz.B; b += gridDim.x) {
+    const float* g = p.rz.feats + b * p.rz.F + p.rz.poff[br];
+    for (int e = threadIdx.x; e < H * W; e += blockDim.x) src[e] = g[e];
+    __syncthreads();
+    for (int e = threadIdx.x; e < H * R; e += blockDim.x) {
+      const int y = e / R, xx = e - y * R;
+      const int2 bd = bh[xx];
+      double ss = 0.0;
+      for (int x = 0; x < bd.y; ++x) ss += static_cast<double>(src[y * W + bd.x + x]) * kh[xx * ksh + x];
+      tmp[e] = static_cast<float>(ss);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < R * R; e += blockDim.x) {
+      const int yy = e / R, xx = e - yy * R;
+      const int2 bd = bv[yy];
+      double ss = 0.0;
+      for (int y = 0; y < bd.y; ++y) ss += static_cast<double>(tmp[(bd.x + y) * R + xx]) * kv[yy * ksv + y];
+      img[e] = static_cast<float>(ss);
+    }
+    __syncthreads();
+    // first tower layer straight from the smem image: a warp per output row, a lane per CPL channels
+    __nv_bfloat16* out = p.out + (b * 3 + br) * static_cast<int64_t>(p.Ho) * p.Wo * p.Cout + lane * CPL;
+    for (int oy = warp; oy < p.Ho; oy += nw) {
+      const int iy0 = oy * 2 - p.pad_t;
+      for (int ox0 = 0; ox0 < p.Wo; ox0 += 4) {
+        const int ix0 = ox0 * 2 - p.pad_l;
+        float x[3][9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int iy = iy0 + r;
+          const bool rowok = iy >= 0 && iy < R;
+#pragma unroll
+          for (int cx = 0; cx < 9; ++cx) {
+            const int ix = ix0 + cx;
+            x[r][cx] = (rowok && ix >= 0 && ix < R) ? img[iy * R + ix] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          if (ox0 + px < p.Wo) {
+            float acc[CPL];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) acc[c] = bs[c];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) acc[c] = fmaf(x[r][2 * px + kw], w[r * 3 + kw][c], acc[c]);
+            __nv_bfloat16* o = out + (static_cast<int64_t>(oy) * p.Wo + ox0 + px) * p.Cout;
+#pragma unroll
+            for (int c = 0; c < CPL; c += 2)
+              *reinterpret_cast<__nv_bfloat162*>(o + c) =
+                  __floats2bfloat162_rn(apply_act(acc[c], p.act, p.alpha), apply_act(acc[c + 1], p.act, p.alpha));
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------ K4 implicit GEMM
 // Conv2D(3x3, strides 2, 'same') for Cin % 64 == 0 as a tcgen05 implicit GEMM:
 //   M = 128 output pixels (a TH x Wo block of one image), N = Cout, K = 9 taps x Cin.

@@ -78,6 +78,7 @@ struct NetConv {
 struct Net {
   bool ready = false;
   bool use_igemm = false;   // layers >= 1 run as tcgen05 implicit GEMMs on bf16 activations
+  bool fuse_resize = true;  // resize + first layer in one kernel (RML_NET_FUSE1=0 disables)
   int R = 0, C = 0, head = 0;
   float alpha = 0.2f;
   std::vector<NetConv> convs;
@@ -1112,6 +1113,7 @@ int rml_net_finish(rml_ctx* c) {
   }
   if (const char* e = getenv("RML_IGEMM")) ok = ok && atoi(e) != 0;
   n.use_igemm = ok;
+  if (const char* e = getenv("RML_NET_FUSE1")) n.fuse_resize = atoi(e) != 0;
   if (ok) {
     for (size_t l = 1; l < n.convs.size(); ++l) {
       NetConv& cv = n.convs[l];
@@ -1236,14 +1238,51 @@ static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_
   float* images = reinterpret_cast<float*>(ws);
   float* ping = reinterpret_cast<float*>(ws + img_b);
   float* pong = reinterpret_cast<float*>(ws + img_b + act_b);
-  if (feats) {
+  const bool fuse1 = feats && n.use_igemm && n.fuse_resize && (n.convs[0].cout == 64 || n.convs[0].cout == 128);
+  if (feats && !fuse1) {
     int rc = net_resize(c, feats, n_scans, images, st);
     if (rc) return rc;
   }
   // K4 conv towers
   const void* cur = feats ? images : images_in;
   int hw = n.R;
-  for (size_t l = 0; l < n.convs.size(); ++l) {
+  size_t l0 = 0;
+  if (fuse1) {
+    // K3 + first tower layer in one kernel: the resized image never leaves shared memory
+    const NetConv& cv = n.convs[0];
+    ResizeConv1Params fp;
+    fp.rz.feats = feats; fp.rz.images = nullptr; fp.rz.B = n_scans; fp.rz.F = feature_len(c, RML_MASK_ALL); fp.rz.R = n.R;
+    const int ph[3] = {c->sx, c->sy, c->sx}, pw[3] = {c->sz, c->sz, c->sy};
+    const int poff[3] = {0, c->sx * c->sz, c->sx * c->sz + c->sy * c->sz};
+    int smem_max = 0;
+    for (int b = 0; b < 3; ++b) {
+      fp.rz.ph[b] = ph[b]; fp.rz.pw[b] = pw[b]; fp.rz.poff[b] = poff[b];
+      fp.rz.kh[b] = n.kh[b]; fp.rz.kv[b] = n.kv[b]; fp.rz.bh[b] = n.bh[b]; fp.rz.bv[b] = n.bv[b];
+      fp.rz.ksh[b] = n.ksh[b]; fp.rz.ksv[b] = n.ksv[b];
+      fp.w[b] = cv.w[b]; fp.bias[b] = cv.bias[b];
+      const int sm = (ph[b] * pw[b] + ph[b] * n.R + n.R * n.R) * 4;
+      if (sm > smem_max) smem_max = sm;
+    }
+    const int ho = (hw + 1) / 2;
+    const int pad_total = (ho - 1) * 2 + 3 - hw;
+    fp.Cout = cv.cout; fp.Ho = ho; fp.Wo = ho; fp.pad_t = fp.pad_l = pad_total > 0 ? pad_total / 2 : 0;
+    fp.act = cv.act; fp.alpha = n.alpha;
+    fp.out = reinterpret_cast<__nv_bfloat16*>(ping);
+    const int gx = static_cast<int>(n_scans < 8ll * c->num_sms ? n_scans : 8ll * c->num_sms);
+    if (cv.cout == 64) {
+      RML_CUDA(c, cudaFuncSetAttribute(k34_resize_conv1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      k34_resize_conv1<2><<<dim3(gx, 3), 256, smem_max, st>>>(fp);
+    } else {
+      RML_CUDA(c, cudaFuncSetAttribute(k34_resize_conv1<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      k34_resize_conv1<4><<<dim3(gx, 3), 256, smem_max, st>>>(fp);
+    }
+    RML_CUDA(c, cudaGetLastError());
+    ++c->launches;
+    cur = ping;
+    hw = ho;
+    l0 = 1;
+  }
+  for (size_t l = l0; l < n.convs.size(); ++l) {
     const NetConv& cv = n.convs[l];
     const bool last = l + 1 == n.convs.size();
     const int ho = (hw + 1) / 2;
