@@ -445,6 +445,87 @@ __global__ void __launch_bounds__(256) k1_project_generic(const K1GenParams p) {
   }
 }
 
+// SLICE projections (predict.py:102-107) for arenas with size_z % 4 == 0: one CTA per scan, every
+// thread keeps four independent 16-byte (xz, yz rows) or 4-byte (xy gather) loads in flight; the
+// three planes are the only bytes touched (59 KB of the 480 KB cube, xy as 32-byte sectors).
+template <typename OutT>
+__device__ __forceinline__ void slice_put4(OutT* out, int idx, float4 v, const K1GenParams& p,
+                                           uint32_t& sumsq, uint32_t& bad);
+template <>
+__device__ __forceinline__ void slice_put4<uint8_t>(uint8_t* out, int idx, float4 v, const K1GenParams&,
+                                                    uint32_t& sumsq, uint32_t& bad) {
+  const uint32_t a = Emit<uint8_t>::cvt(v.x, bad), b = Emit<uint8_t>::cvt(v.y, bad);
+  const uint32_t c = Emit<uint8_t>::cvt(v.z, bad), d = Emit<uint8_t>::cvt(v.w, bad);
+  sumsq += a * a + b * b + c * c + d * d;
+  *reinterpret_cast<uint32_t*>(out + idx) = a | (b << 8) | (c << 16) | (d << 24);
+}
+template <>
+__device__ __forceinline__ void slice_put4<float>(float* out, int idx, float4 v, const K1GenParams& p,
+                                                  uint32_t&, uint32_t&) {
+  if (p.affine) {
+    v.x = __fdiv_rn(v.x - p.offset, p.scale); v.y = __fdiv_rn(v.y - p.offset, p.scale);
+    v.z = __fdiv_rn(v.z - p.offset, p.scale); v.w = __fdiv_rn(v.w - p.offset, p.scale);
+  }
+  out[idx] = v.x; out[idx + 1] = v.y; out[idx + 2] = v.z; out[idx + 3] = v.w;   // rows are 8-B aligned only
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) k1_project_slice(const K1GenParams p) {
+  __shared__ uint32_t s_sum;
+  const int sx = p.sx, sy = p.sy, sz = p.sz, zq = sz >> 2;
+  const int fxz = sx * sz, fyz = sy * sz, fxy = sx * sy;
+  const int off_yz = (p.mask & 1u) ? fxz : 0;
+  const int off_xy = off_yz + ((p.mask & 2u) ? fyz : 0);
+  const int n_xz = (p.mask & 1u) ? sx * zq : 0;      // float4 items
+  const int n_yz = (p.mask & 2u) ? sy * zq : 0;
+  const int n_xy = (p.mask & 4u) ? fxy : 0;           // scalar items
+  const int n_items = n_xz + n_yz + n_xy;
+  for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const float* cube = p.cubes + b * static_cast<int64_t>(sx) * sy * sz;
+    OutT* out = reinterpret_cast<OutT*>(p.feats) + b * static_cast<int64_t>(p.stride);
+    int ti = p.ijk[b * 3 + 0], tj = p.ijk[b * 3 + 1], tk = p.ijk[b * 3 + 2];
+    if (ti < 0) ti += sx;                       // numpy: negative indices wrap once
+    if (tj < 0) tj += sy;
+    if (tk < 0) tk += sz;
+    const bool ok = ti >= 0 && ti < sx && tj >= 0 && tj < sy && tk >= 0 && tk < sz;
+    if (!ok) {
+      if (threadIdx.x == 0) atomicAdd(p.status + 1, 1u);   // numpy would raise IndexError
+      ti = tj = tk = 0;
+    }
+    uint32_t sumsq = 0, bad = 0;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < n_items; e += 256) {
+      if (e < n_xz) {
+        const int i = e / zq, c = e - i * zq;
+        float4 v = *reinterpret_cast<const float4*>(cube + (static_cast<int64_t>(i) * sy + tj) * sz + 4 * c);
+        if (!ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        slice_put4<OutT>(out, i * sz + 4 * c, v, p, sumsq, bad);
+      } else if (e < n_xz + n_yz) {
+        const int r = e - n_xz;
+        const int j = r / zq, c = r - j * zq;
+        float4 v = *reinterpret_cast<const float4*>(cube + (static_cast<int64_t>(ti) * sy + j) * sz + 4 * c);
+        if (!ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        slice_put4<OutT>(out, off_yz + j * sz + 4 * c, v, p, sumsq, bad);
+      } else {
+        const int r = e - n_xz - n_yz;
+        const float v = ok ? cube[static_cast<int64_t>(r) * sz + tk] : 0.f;
+        gen_put<OutT>(out, off_xy + r, v, p, sumsq, bad);
+      }
+    }
+    if (sizeof(OutT) == 1) {
+      for (int e = p.F + threadIdx.x; e < p.stride; e += blockDim.x) out[e] = 0;
+      const uint32_t tot = __reduce_add_sync(0xffffffffu, sumsq);
+      if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&s_sum, tot);
+      __syncthreads();
+      if (threadIdx.x == 0 && p.norms) p.norms[b] = static_cast<int32_t>(s_sum);
+      if (bad) atomicAdd(p.status, 1u);
+    }
+    __syncthreads();
+  }
+}
+
 // common.process_samples on already extracted projections (common.py:141-149, zoom 1.0).
 struct PsParams {
   const float* proj[3];  // xz, yz, xy (nullable when masked out)

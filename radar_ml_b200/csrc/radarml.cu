@@ -309,8 +309,14 @@ int project_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
     p.offset = aff.offset; p.scale = aff.scale; p.affine = aff.enabled; p.mode = mode;
     const int64_t want = B < 8ll * c->num_sms ? B : 8ll * c->num_sms;
     const int grid = static_cast<int>(want);
-    if (dtype == RML_U8) k1_project_generic<uint8_t><<<grid, 256, 0, st>>>(p);
-    else k1_project_generic<float><<<grid, 256, 0, st>>>(p);
+    const bool vec_slice = mode == RML_MODE_SLICE && (c->sz & 3) == 0 && (dtype != RML_U8 || (stride & 3) == 0);
+    if (vec_slice) {
+      if (dtype == RML_U8) k1_project_slice<uint8_t><<<grid, 256, 0, st>>>(p);
+      else k1_project_slice<float><<<grid, 256, 0, st>>>(p);
+    } else {
+      if (dtype == RML_U8) k1_project_generic<uint8_t><<<grid, 256, 0, st>>>(p);
+      else k1_project_generic<float><<<grid, 256, 0, st>>>(p);
+    }
   }
   RML_CUDA(c, cudaGetLastError());
   ++c->launches;

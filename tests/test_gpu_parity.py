@@ -559,3 +559,34 @@ def test_multidigit_scorer_on_nonintegral_data(eng):
         eng.check_status()
     P_bad = restate.predict_proba(bad, p)
     assert np.abs(gm.predict_proba(bad) - P_bad).max() < PROBA_TOL
+
+
+@pytest.mark.parametrize("dims", [(10, 12, 40), (7, 9, 30), (22, 31, 176)])
+def test_other_arenas_max_and_slice(dims):
+    """rml_set_arena: any cube size goes through the generic / vectorised-slice kernels."""
+    import torch
+    from oracle import restate
+    from radar_ml_b200.engine import Engine
+    e = Engine(0)
+    sx, sy, sz = dims
+    e.set_arena(sx, sy, sz)
+    rng = np.random.default_rng(sx * sz)
+    n = 37
+    cubes = rng.integers(0, 256, (n, sx, sy, sz)).astype(np.float32)
+    ijk = np.stack([rng.integers(-sx, sx, n), rng.integers(-sy, sy, n), rng.integers(-sz, sz, n)], axis=1).astype(np.int32)
+    d = torch.from_numpy(cubes).cuda()
+    for mask in ((True, True, True), (False, True, True), (True, False, False)):
+        for mode in ("max", "slice"):
+            want = np.asarray([restate.process_samples(
+                [restate.project(cubes[s], mode, tuple(int(v) for v in ijk[s]))],
+                proj_mask=restate.ProjMask(*mask), scale=True)[0] for s in range(n)], dtype=np.float32)
+            got = e.project(d, mode=mode, ijk=torch.from_numpy(ijk).cuda(), mask=mask).cpu().numpy()
+            assert got.shape == want.shape and np.array_equal(got, want), (dims, mask, mode)
+            q, norms = e.project(d, mode=mode, ijk=torch.from_numpy(ijk).cuda(), mask=mask, dtype=1)
+            e.check_status()
+            F = want.shape[1]
+            raw = np.rint(want * 255.0)
+            assert np.array_equal(q.cpu().numpy()[:, :F].astype(np.float32), raw), (dims, mask, mode)
+            assert not q.cpu().numpy()[:, F:].any()
+            assert np.array_equal(norms.cpu().numpy().astype(np.int64), (raw.astype(np.int64) ** 2).sum(axis=1))
+    e.close()
