@@ -39,17 +39,47 @@ __global__ void __launch_bounds__(256) k0_derive_targets(const DeriveParams p) {
     for (int e = threadIdx.x; e < p.sx + p.sy + p.sz + nw * p.sz; e += blockDim.x) ds[e] = 0.f;
     __syncthreads();
     const float* cube = p.cubes + b * static_cast<int64_t>(rows) * p.sz;
-    for (int r = warp; r < rows; r += nw) {
-      const float* row = cube + static_cast<int64_t>(r) * p.sz;
-      float s = 0.f;
-      for (int k = lane; k < p.sz; k += 32) {
-        const float v = row[k];
-        s += v;
-        part[warp * p.sz + k] += v;          // this lane owns column k of this warp's partial
-      }
+    // four rows per warp step, all loads issued before the adds (memory-level parallelism)
+    for (int r0 = warp * 4; r0 < rows; r0 += nw * 4) {
+      float v[4][6];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) rowsum[r] = s;
+      for (int u = 0; u < 4; ++u) {
+        const float* row = cube + static_cast<int64_t>(r0 + u) * p.sz;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const int k = lane + 32 * q;
+          v[u][q] = (r0 + u < rows && k < p.sz) ? row[k] : 0.f;
+        }
+      }
+      if (p.sz <= 192) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float s = 0.f;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            s += v[u][q];
+            const int k = lane + 32 * q;
+            if (k < p.sz) part[warp * p.sz + k] += v[u][q];
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0 && r0 + u < rows) rowsum[r0 + u] = s;
+        }
+      } else {
+        // wide rows: the generic strided walk
+        for (int u = 0; u < 4 && r0 + u < rows; ++u) {
+          const float* row = cube + static_cast<int64_t>(r0 + u) * p.sz;
+          float s = 0.f;
+          for (int k = lane; k < p.sz; k += 32) {
+            const float x = row[k];
+            s += x;
+            part[warp * p.sz + k] += x;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0) rowsum[r0 + u] = s;
+        }
+      }
     }
     __syncthreads();
     // fixed summation order: results are reproducible run to run
