@@ -47,6 +47,7 @@ struct K1Params {
   uint32_t mask;
   float offset, scale;  // f32 output: (v - offset) / scale when affine != 0
   int affine;
+  int split;                // bulk copies per slab (1; 2 / 4 are tuning experiments)
   unsigned int* tile_done;  // nullable: [ceil(B/128)] += 1 per finished scan (u8 path) so a
                             // co-resident scorer can start on a 128-scan tile as soon as it is whole
 };
@@ -286,7 +287,10 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
           const int stage = it % kK1Stages;
           mbar_wait(&empty[stage], ((it / kK1Stages) & 1) ^ 1);
           mbar_arrive_expect_tx(&full[stage], kSlabBytes);
-          bulk_g2s(slabs + stage * kSlabElems, cube + i * kSlabElems, kSlabBytes, &full[stage], pol);
+          const int part = kSlabElems / p.split;
+          for (int q = 0; q < p.split; ++q)
+            bulk_g2s(slabs + stage * kSlabElems + q * part, cube + i * kSlabElems + q * part, part * 4,
+                     &full[stage], pol);
         }
       }
     }

@@ -291,6 +291,8 @@ int project_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
     p.stride = stride; p.F = F; p.mask = mask;
     p.offset = aff.offset; p.scale = aff.scale; p.affine = aff.enabled;
     p.tile_done = dtype == RML_U8 ? tile_done : nullptr;
+    p.split = 1;
+    if (const char* e = getenv("RML_K1_SPLIT")) { const int v = atoi(e); if (v == 2 || v == 4) p.split = v; }
     const int sms = grid_limit > 0 ? grid_limit : c->num_sms;
     const int grid = static_cast<int>(B < sms ? B : sms);
     if (dtype == RML_U8) {
