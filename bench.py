@@ -49,7 +49,7 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def device_cubes(n, seed, device, chunk=1024):
+def device_cubes(n, seed, device, chunk=1024, integer=True):
     """Integer-valued sparse-blob cubes generated ON the device: one anisotropic
     Gaussian blob per scan, amplitude U(.5,1)*255, N(0,6) noise, rint, <13 -> 0, clip [0,255]."""
     import torch
@@ -73,9 +73,10 @@ def device_cubes(n, seed, device, chunk=1024):
                                     + ((gj - cj) / s[:, 1].view(m, 1, 1, 1)) ** 2
                                     + ((gk - ck) / s[:, 2].view(m, 1, 1, 1)) ** 2))
         v += 6.0 * torch.randn(v.shape, device=device, generator=g)
-        v = torch.round(v)
-        v[v < 13.0] = 0.0
-        out[lo:lo + m] = v.clamp_(0.0, 255.0)
+        if integer:
+            v = torch.round(v)
+            v[v < 13.0] = 0.0
+        out[lo:lo + m] = v.clamp_(0.0, 255.0)      # integer=False: real-valued scans, still in range
         del v
     return out
 
@@ -142,7 +143,8 @@ def build_model(seed=1234):
     n_train = int(os.environ.get("RML_BENCH_TRAIN", "909"))     # test hook: a smaller fit
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        return synth.standard_model(n_train=n_train, n_val=max(30, n_train // 8), seed=seed, mode="max")
+        n_val = 114 if n_train == 909 else max(30, n_train // 8)      # train_svc.log:11-13 split sizes
+        return synth.standard_model(n_train=n_train, n_val=n_val, seed=seed, mode="max")
 
 
 # ------------------------------------------------------------------------------ reference arm
@@ -326,6 +328,40 @@ def run_ours(args):
                    "sample": "%d of the GPU-scored scans, per-scan predict.py loop, one process per "
                              "core, sklearn libsvm (%.1f s)" % (sample, dt)}
 
+    # ---- general-precision case: real-valued cubes + non-integral support vectors
+    general = None
+    if rank == 0 and world == 1:
+        import copy
+        p2 = copy.deepcopy(params)
+        wob = 3e-5 * np.sin(np.arange(p2.sv.size, dtype=np.float64)).reshape(p2.sv.shape)
+        p2.sv = np.clip(p2.sv + wob, 0.0, 1.0)                 # like augmented training data
+        eng2 = Engine(local)
+        eng2.load_model(p2)
+        assert not eng2.model_is_integral
+        Bg = 16384
+        cg = device_cubes(Bg, 777, dev, integer=False)
+        outg = eng2.predict(cg)
+        eng2.check_status()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        g0.record(stream)
+        for _ in range(5):
+            eng2.predict(cg, out=outg)
+        g1.record(stream)
+        torch.cuda.synchronize(dev)
+        gms = g0.elapsed_time(g1) / 5
+        po = restate.export_params(cal)
+        po.sv = p2.sv
+        ng = 96
+        _, lab_o, _, _, P_o = restate.scan_path(cg[:ng].cpu().numpy(), po, mode="max")
+        general = {"workload": "16384 real-valued cubes, non-integral support vectors: K1 f32 -> 24-bit "
+                               "fixed-point digit planes -> exact multi-digit tcgen05 scorer",
+                   "value": Bg / gms * 1e3, "unit": "scans/s", "ms_per_step": gms,
+                   "labels_equal": bool(np.array_equal(outg[1][:ng].cpu().numpy(), lab_o)),
+                   "max_abs_dproba": float(np.abs(outg[0][:ng].cpu().numpy().astype(np.float64) - P_o).max())}
+        del cg
+        eng2.close()
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         k1_gbs = B * CUBE_BYTES / (k1_ms * 1e-3) / 1e9
@@ -355,6 +391,8 @@ def run_ours(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if general:
+            line["general_precision"] = general
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
