@@ -362,6 +362,57 @@ def run_ours(args):
         del cg
         eng2.close()
 
+    # ---- uint8 cubes (the sensor's integers kept as bytes; include/radarml.h rml_predict*_u8):
+    # same scans, a quarter of the bytes over PCIe and HBM, results identical bit for bit
+    u8leg = None
+    if rank == 0 and world == 1 and os.environ.get("RML_BENCH_U8", "1") != "0":
+        host8 = torch.empty((Be, 22, 31, 176), dtype=torch.uint8, pin_memory=True)
+        host8.copy_(cubes[:Be].to(torch.uint8))
+        torch.cuda.synchronize(dev)
+        host8_np = host8.numpy()
+        out8 = (np.empty((Be, C), np.float32), np.empty((Be,), np.int32), np.empty((Be,), np.uint8))
+        for _ in range(2):
+            eng.predict_host(host8_np, mode="max", out=out8)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.predict_host(host8_np, mode="max", out=out8)
+        e2e8_s = time.perf_counter() - t0
+        cubes8 = torch.empty((B, 22, 31, 176), device=dev, dtype=torch.uint8)
+        for lo in range(0, B, 4096):
+            cubes8[lo:lo + 4096] = cubes[lo:lo + 4096].to(torch.uint8)
+        res8 = eng.predict(cubes8)
+        eng.check_status()
+        for _ in range(2):
+            eng.predict(cubes8, out=res8)
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        u0.record(stream)
+        for _ in range(args.steps):
+            eng.predict(cubes8, out=res8)
+        u1.record(stream)
+        torch.cuda.synchronize(dev)
+        u8_ms = u0.elapsed_time(u1) / args.steps
+        k1u = []
+        for _ in range(5):
+            eng.predict(cubes8, out=res8)
+            rc = lib.rml_last_timing(ctx, Ct.byref(k1v), Ct.byref(totv), Ct.byref(fusedv))
+            assert rc == 0, lib.rml_last_error(ctx)
+            k1u.append(k1v.value)
+        k1u_ms = float(np.mean(k1u))
+        peak_u, _ = measured_peaks()
+        u8leg = {"workload": "the same scans held as uint8 cubes (120 032 B/scan)",
+                 "e2e": {"value": Be * args.steps / e2e8_s, "unit": "scans/s",
+                         "h2d_bytes_per_step": Be * CUBE_BYTES // 4, "d2h_bytes_per_step": Be * (4 * C + 4 + 1)},
+                 "value": B / u8_ms * 1e3, "unit": "scans/s", "ms_per_step": u8_ms,
+                 "roofline": {"bound": "hbm", "kernel": "k1_project_max_u8in<u8>",
+                              "achieved": B * (CUBE_BYTES // 4) / (k1u_ms * 1e-3) / 1e9, "peak": peak_u,
+                              "unit": "GB/s", "frac": B * (CUBE_BYTES // 4) / (k1u_ms * 1e-3) / 1e9 / peak_u,
+                              "k1_ms": k1u_ms, "fused_pipeline": bool(fusedv.value)},
+                 "labels_equal_f32_path": bool(torch.equal(res8[1], label)),
+                 "proba_equal_f32_path": bool(torch.equal(res8[0], proba)),
+                 "e2e_labels_equal": bool(np.array_equal(out8[1], e2e_labels))}
+        del cubes8, host8
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         k1_gbs = B * CUBE_BYTES / (k1_ms * 1e-3) / 1e9
@@ -393,6 +444,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if general:
             line["general_precision"] = general
+        if u8leg:
+            line["u8_cubes"] = u8leg
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

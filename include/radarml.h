@@ -159,6 +159,23 @@ int rml_predict_host(rml_ctx* ctx, const float* cubes_host, int64_t B, int mode,
                      const int32_t* ijk_host, uint32_t mask, double min_proba, float* proba_host,
                      int32_t* label_host, uint8_t* known_host);
 
+/* ---- uint8 cubes: the sensor's integers kept as bytes ----------------------------------- */
+/* predict.py:90-91 widens the Walabot's integer voxels (0..255, ground_truth_samples.py:352)
+ * with np.array(raw_image, dtype=np.float32).  A caller that holds them as uint8
+ * (np.array(raw_image, dtype=np.uint8)) moves a quarter of the bytes over PCIe and HBM; the
+ * results are those of the float32 entry points on the widened cube, bit for bit.
+ * cubes: uint8 [B][size_x][size_y][size_z], same axis order; everything else as in
+ * rml_project / rml_predict / rml_predict_host / rml_net_predict. */
+int rml_project_u8(rml_ctx* ctx, const uint8_t* cubes_dev, int64_t B, int mode,
+                   const int32_t* ijk_dev, uint32_t mask, int dtype, void* feats_dev,
+                   int32_t* norms_dev, rml_stream stream);
+int rml_predict_u8(rml_ctx* ctx, const uint8_t* cubes_dev, int64_t B, int mode,
+                   const int32_t* ijk_dev, uint32_t mask, double min_proba, void* workspace_dev,
+                   float* proba_dev, int32_t* label_dev, uint8_t* known_dev, rml_stream stream);
+int rml_predict_host_u8(rml_ctx* ctx, const uint8_t* cubes_host, int64_t B, int mode,
+                        const int32_t* ijk_host, uint32_t mask, double min_proba,
+                        float* proba_host, int32_t* label_host, uint8_t* known_host);
+
 /* ---- dnn.py / sgan.py classifier forward ------------------------ */
 /* Load sequence: begin -> resize tables x3 -> conv layers (per layer, per branch) -> dense ->
  * finish.  All pointers are HOST pointers.  BatchNorm (sgan.py:138,144,150,190,195) is folded
@@ -209,6 +226,10 @@ int rml_net_predict(rml_ctx* ctx, const float* cubes_dev, int64_t B, int mode,
                     const int32_t* ijk_dev, void* workspace_dev, size_t workspace_bytes,
                     float* proba_dev, int32_t* label_dev, rml_stream stream);
 
+int rml_net_predict_u8(rml_ctx* ctx, const uint8_t* cubes_dev, int64_t B, int mode,
+                       const int32_t* ijk_dev, void* workspace_dev, size_t workspace_bytes,
+                       float* proba_dev, int32_t* label_dev, rml_stream stream);
+
 /* ---- status of the last asynchronous work (non-integral count seen by the u8 path) ----- */
 int rml_check_status(rml_ctx* ctx, rml_stream stream); /* synchronises the stream */
 
@@ -217,6 +238,8 @@ int rml_check_status(rml_ctx* ctx, rml_stream stream); /* synchronises the strea
  * scorer is co-resident on the other k2_sms SMs and starts a tile the moment it is complete.
  * enabled=0 forces the serial K1 -> K2 order (also: env RML_FUSED=0, RML_K2_SMS, RML_FUSED_MIN_B). */
 int rml_set_fused(rml_ctx* ctx, int enabled, int k2_sms, int64_t min_batch);
+/* scorer SMs when the cubes are uint8 (they stream 4x faster; also env RML_K2_SMS_U8) */
+int rml_set_fused_u8(rml_ctx* ctx, int k2_sms);
 /* CUDA-event timing of the kernels inside the last rml_predict on this context: k1_ms =
  * projection kernel alone, total_ms = projection start -> scorer end.  Synchronises. */
 int rml_enable_timing(rml_ctx* ctx, int enabled);

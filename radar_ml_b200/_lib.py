@@ -88,6 +88,11 @@ SIGNATURES = {
     "rml_predict_workspace_bytes": (_sz, [_vp, _i64]),
     "rml_predict": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _u32, _f64, _vp, _vp, _vp, _vp, _vp]),
     "rml_predict_host": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _u32, _f64, _vp, _vp, _vp]),
+    "rml_project_u8": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _u32, C.c_int, _vp, _vp, _vp]),
+    "rml_predict_u8": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _u32, _f64, _vp, _vp, _vp, _vp, _vp]),
+    "rml_predict_host_u8": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _u32, _f64, _vp, _vp, _vp]),
+    "rml_net_predict_u8": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "rml_set_fused_u8": (C.c_int, [_vp, C.c_int]),
     "rml_net_begin": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32]),
     "rml_net_set_resize_tables": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp]),
     "rml_net_add_conv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),

@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
 // Generic kernels: any arena, MAX or SLICE (predict.py:102-107 semantics incl. numpy negative
 // index wrap).  One CTA per scan; SLICE touches only the three planes it needs.
 struct K1GenParams {
-  const float* cubes;
+  const void* cubes;   // float32 or uint8 voxels (the kernels' InT)
   const int32_t* ijk;  // [B][3] (slice)
   void* feats;
   int32_t* norms;
@@ -363,7 +363,7 @@ __device__ __forceinline__ void gen_put<float>(float* out, int idx, float v, con
   out[idx] = p.affine ? __fdiv_rn(v - p.offset, p.scale) : v;
 }
 
-template <typename OutT>
+template <typename OutT, typename InT = float>
 __global__ void __launch_bounds__(256) k1_project_generic(const K1GenParams p) {
   __shared__ uint32_t s_sum;
   const int sx = p.sx, sy = p.sy, sz = p.sz;
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256) k1_project_generic(const K1GenParams p) {
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     if (threadIdx.x == 0) s_sum = 0;
     __syncthreads();
-    const float* cube = p.cubes + b * static_cast<int64_t>(sx) * sy * sz;
+    const InT* cube = static_cast<const InT*>(p.cubes) + b * static_cast<int64_t>(sx) * sy * sz;
     OutT* out = reinterpret_cast<OutT*>(p.feats) + b * static_cast<int64_t>(p.stride);
     uint32_t sumsq = 0, bad = 0;
     int ti = 0, tj = 0, tk = 0;
@@ -397,10 +397,10 @@ __global__ void __launch_bounds__(256) k1_project_generic(const K1GenParams p) {
         const int i = e / sz, k = e - i * sz;
         float v;
         if (p.mode == 1) {
-          v = cube[(static_cast<int64_t>(i) * sy + tj) * sz + k];
+          v = static_cast<float>(cube[(static_cast<int64_t>(i) * sy + tj) * sz + k]);
         } else {
           v = -FLT_MAX;
-          for (int j = 0; j < sy; ++j) v = fmaxf(v, cube[(static_cast<int64_t>(i) * sy + j) * sz + k]);
+          for (int j = 0; j < sy; ++j) v = fmaxf(v, static_cast<float>(cube[(static_cast<int64_t>(i) * sy + j) * sz + k]));
         }
         gen_put<OutT>(out, e, ok ? v : 0.f, p, sumsq, bad);
       }
@@ -410,10 +410,10 @@ __global__ void __launch_bounds__(256) k1_project_generic(const K1GenParams p) {
         const int j = e / sz, k = e - j * sz;
         float v;
         if (p.mode == 1) {
-          v = cube[(static_cast<int64_t>(ti) * sy + j) * sz + k];
+          v = static_cast<float>(cube[(static_cast<int64_t>(ti) * sy + j) * sz + k]);
         } else {
           v = -FLT_MAX;
-          for (int i = 0; i < sx; ++i) v = fmaxf(v, cube[(static_cast<int64_t>(i) * sy + j) * sz + k]);
+          for (int i = 0; i < sx; ++i) v = fmaxf(v, static_cast<float>(cube[(static_cast<int64_t>(i) * sy + j) * sz + k]));
         }
         gen_put<OutT>(out, off_yz + e, ok ? v : 0.f, p, sumsq, bad);
       }
@@ -421,16 +421,16 @@ __global__ void __launch_bounds__(256) k1_project_generic(const K1GenParams p) {
     if (p.mask & 4u) {
       if (p.mode == 1) {
         for (int e = threadIdx.x; e < fxy; e += blockDim.x) {
-          const float v = cube[static_cast<int64_t>(e) * sz + tk];
+          const float v = static_cast<float>(cube[static_cast<int64_t>(e) * sz + tk]);
           gen_put<OutT>(out, off_xy + e, ok ? v : 0.f, p, sumsq, bad);
         }
       } else {
         // one warp per (i,j) row: coalesced read along k, shuffle max
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
         for (int e = warp; e < fxy; e += nw) {
-          const float* row = cube + static_cast<int64_t>(e) * sz;
+          const InT* row = cube + static_cast<int64_t>(e) * sz;
           float v = -FLT_MAX;
-          for (int k = lane; k < sz; k += 32) v = fmaxf(v, row[k]);
+          for (int k = lane; k < sz; k += 32) v = fmaxf(v, static_cast<float>(row[k]));
           v = warp_max_f32(v);
           if (lane == 0) gen_put<OutT>(out, off_xy + e, v, p, sumsq, bad);
         }
@@ -473,7 +473,20 @@ __device__ __forceinline__ void slice_put4<float>(float* out, int idx, float4 v,
   out[idx] = v.x; out[idx + 1] = v.y; out[idx + 2] = v.z; out[idx + 3] = v.w;   // rows are 8-B aligned only
 }
 
-template <typename OutT>
+template <typename InT>
+__device__ __forceinline__ float4 slice_load4(const InT* q);
+template <>
+__device__ __forceinline__ float4 slice_load4<float>(const float* q) {
+  return *reinterpret_cast<const float4*>(q);
+}
+template <>
+__device__ __forceinline__ float4 slice_load4<uint8_t>(const uint8_t* q) {
+  const uchar4 u = *reinterpret_cast<const uchar4*>(q);
+  return make_float4(static_cast<float>(u.x), static_cast<float>(u.y), static_cast<float>(u.z),
+                     static_cast<float>(u.w));
+}
+
+template <typename OutT, typename InT = float>
 __global__ void __launch_bounds__(256) k1_project_slice(const K1GenParams p) {
   __shared__ uint32_t s_sum;
   const int sx = p.sx, sy = p.sy, sz = p.sz, zq = sz >> 2;
@@ -487,7 +500,7 @@ __global__ void __launch_bounds__(256) k1_project_slice(const K1GenParams p) {
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     if (threadIdx.x == 0) s_sum = 0;
     __syncthreads();
-    const float* cube = p.cubes + b * static_cast<int64_t>(sx) * sy * sz;
+    const InT* cube = static_cast<const InT*>(p.cubes) + b * static_cast<int64_t>(sx) * sy * sz;
     OutT* out = reinterpret_cast<OutT*>(p.feats) + b * static_cast<int64_t>(p.stride);
     int ti = p.ijk[b * 3 + 0], tj = p.ijk[b * 3 + 1], tk = p.ijk[b * 3 + 2];
     if (ti < 0) ti += sx;                       // numpy: negative indices wrap once
@@ -503,18 +516,18 @@ __global__ void __launch_bounds__(256) k1_project_slice(const K1GenParams p) {
     for (int e = threadIdx.x; e < n_items; e += 256) {
       if (e < n_xz) {
         const int i = e / zq, c = e - i * zq;
-        float4 v = *reinterpret_cast<const float4*>(cube + (static_cast<int64_t>(i) * sy + tj) * sz + 4 * c);
+        float4 v = slice_load4<InT>(cube + (static_cast<int64_t>(i) * sy + tj) * sz + 4 * c);
         if (!ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
         slice_put4<OutT>(out, i * sz + 4 * c, v, p, sumsq, bad);
       } else if (e < n_xz + n_yz) {
         const int r = e - n_xz;
         const int j = r / zq, c = r - j * zq;
-        float4 v = *reinterpret_cast<const float4*>(cube + (static_cast<int64_t>(ti) * sy + j) * sz + 4 * c);
+        float4 v = slice_load4<InT>(cube + (static_cast<int64_t>(ti) * sy + j) * sz + 4 * c);
         if (!ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
         slice_put4<OutT>(out, off_yz + j * sz + 4 * c, v, p, sumsq, bad);
       } else {
         const int r = e - n_xz - n_yz;
-        const float v = ok ? cube[static_cast<int64_t>(r) * sz + tk] : 0.f;
+        const float v = ok ? static_cast<float>(cube[static_cast<int64_t>(r) * sz + tk]) : 0.f;
         gen_put<OutT>(out, off_xy + r, v, p, sumsq, bad);
       }
     }

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include "k1_project.cuh"
+#include "k1_project_u8.cuh"
 #include "k2_score.cuh"
 #include "k2_digits.cuh"
 #include "k3_net.cuh"
@@ -56,7 +57,8 @@ struct Model {
 constexpr int kHostBufs = 3;
 struct HostPipe {
   int64_t chunk = 0;
-  float* cubes[kHostBufs] = {nullptr};
+  size_t cube_bytes = 0;   // bytes per cube the buffers were sized for
+  void* cubes[kHostBufs] = {nullptr};
   int32_t* ijk[kHostBufs] = {nullptr};
   void* work[kHostBufs] = {nullptr};
   float* proba[kHostBufs] = {nullptr};
@@ -114,6 +116,7 @@ struct rml_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_k1a = nullptr, ev_k1b = nullptr, ev_k2b = nullptr;
   unsigned int* tile_done = nullptr;
   int64_t tile_done_cap = 0;
+  int k2_sms_u8 = 48;        // same for uint8 cubes (RML_K2_SMS_U8)
   int k2_sms = 32;           // SMs reserved for the scorer in fused mode (RML_K2_SMS); set from the SM count in rml_create
   int64_t fused_min_b = 8192;
   int fused_enabled = 1;     // RML_FUSED=0 disables
@@ -269,9 +272,11 @@ struct Affine {
   int enabled;
 };
 
-int project_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int32_t* ijk,
+// cubes: float32 voxels (predict.py:91) or, with cube_u8 != 0, the sensor's integers as uint8
+int project_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32_t* ijk,
                  uint32_t mask, int dtype, void* feats, int32_t* norms, cudaStream_t st,
-                 int grid_limit = 0, unsigned int* tile_done = nullptr, const Affine* aff_in = nullptr) {
+                 int grid_limit = 0, unsigned int* tile_done = nullptr, const Affine* aff_in = nullptr,
+                 int cube_u8 = 0) {
   const Affine aff = aff_in ? *aff_in : Affine{c->aff_offset, c->aff_scale, c->aff_enabled};
   if (B < 0 || !cubes || !feats) return fail(c, RML_E_INVALID, "rml_project: null buffer or B<0");
   if ((mask & RML_MASK_ALL) == 0 || (mask & ~RML_MASK_ALL))
@@ -279,15 +284,35 @@ int project_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
   if (mode != RML_MODE_MAX && mode != RML_MODE_SLICE) return fail(c, RML_E_INVALID, "bad mode %d", mode);
   if (mode == RML_MODE_SLICE && !ijk) return fail(c, RML_E_INVALID, "SLICE mode needs ijk");
   if (dtype != RML_F32 && dtype != RML_U8) return fail(c, RML_E_INVALID, "bad dtype %d", dtype);
-  if ((reinterpret_cast<uintptr_t>(cubes) & 15) || (reinterpret_cast<uintptr_t>(feats) & 15))
+  const bool fast = mode == RML_MODE_MAX && c->sx == kSX && c->sy == kSY && c->sz == kSZ;
+  // bulk copies / float4 loads need 16-byte granules; uint8 cubes outside the streaming kernel
+  // are read as uchar4 at most
+  const uintptr_t cube_align = (cube_u8 && !fast) ? 3 : 15;
+  if ((reinterpret_cast<uintptr_t>(cubes) & cube_align) || (reinterpret_cast<uintptr_t>(feats) & 15))
     return fail(c, RML_E_INVALID, "cubes/feats must be 16-byte aligned");
   if (B == 0) return RML_OK;
   const int F = feature_len(c, mask);
   const int stride = feature_stride(c, mask, dtype);
-  const bool fast = mode == RML_MODE_MAX && c->sx == kSX && c->sy == kSY && c->sz == kSZ;
-  if (fast) {
+  if (fast && cube_u8) {
+    K1U8Params p;
+    p.cubes = static_cast<const uint8_t*>(cubes); p.feats = feats; p.norms = norms; p.B = B;
+    p.stride = stride; p.F = F; p.mask = mask;
+    p.offset = aff.offset; p.scale = aff.scale; p.affine = aff.enabled;
+    p.tile_done = dtype == RML_U8 ? tile_done : nullptr;
+    const int sms = grid_limit > 0 ? grid_limit : c->num_sms;
+    const int grid = static_cast<int>(B < sms ? B : sms);
+    if (dtype == RML_U8) {
+      const int smem = k1u8_smem_bytes<uint8_t>();
+      RML_CUDA(c, cudaFuncSetAttribute(k1_project_max_u8in<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k1_project_max_u8in<uint8_t><<<grid, kK1Threads, smem, st>>>(p);
+    } else {
+      const int smem = k1u8_smem_bytes<float>();
+      RML_CUDA(c, cudaFuncSetAttribute(k1_project_max_u8in<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k1_project_max_u8in<float><<<grid, kK1Threads, smem, st>>>(p);
+    }
+  } else if (fast) {
     K1Params p;
-    p.cubes = cubes; p.feats = feats; p.norms = norms; p.status = c->status; p.B = B;
+    p.cubes = static_cast<const float*>(cubes); p.feats = feats; p.norms = norms; p.status = c->status; p.B = B;
     p.stride = stride; p.F = F; p.mask = mask;
     p.offset = aff.offset; p.scale = aff.scale; p.affine = aff.enabled;
     p.tile_done = dtype == RML_U8 ? tile_done : nullptr;
@@ -313,11 +338,21 @@ int project_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
     const int grid = static_cast<int>(want);
     const bool vec_slice = mode == RML_MODE_SLICE && (c->sz & 3) == 0 && (dtype != RML_U8 || (stride & 3) == 0);
     if (vec_slice) {
-      if (dtype == RML_U8) k1_project_slice<uint8_t><<<grid, 256, 0, st>>>(p);
-      else k1_project_slice<float><<<grid, 256, 0, st>>>(p);
+      if (cube_u8) {
+        if (dtype == RML_U8) k1_project_slice<uint8_t, uint8_t><<<grid, 256, 0, st>>>(p);
+        else k1_project_slice<float, uint8_t><<<grid, 256, 0, st>>>(p);
+      } else {
+        if (dtype == RML_U8) k1_project_slice<uint8_t, float><<<grid, 256, 0, st>>>(p);
+        else k1_project_slice<float, float><<<grid, 256, 0, st>>>(p);
+      }
     } else {
-      if (dtype == RML_U8) k1_project_generic<uint8_t><<<grid, 256, 0, st>>>(p);
-      else k1_project_generic<float><<<grid, 256, 0, st>>>(p);
+      if (cube_u8) {
+        if (dtype == RML_U8) k1_project_generic<uint8_t, uint8_t><<<grid, 256, 0, st>>>(p);
+        else k1_project_generic<float, uint8_t><<<grid, 256, 0, st>>>(p);
+      } else {
+        if (dtype == RML_U8) k1_project_generic<uint8_t, float><<<grid, 256, 0, st>>>(p);
+        else k1_project_generic<float, float><<<grid, 256, 0, st>>>(p);
+      }
     }
   }
   RML_CUDA(c, cudaGetLastError());
@@ -409,9 +444,9 @@ bool use_u8_path(const rml_ctx* c) {
   return c->model.kind == 2 || (c->model.kind == 1 && c->model.integral);
 }
 
-int predict_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int32_t* ijk,
+int predict_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32_t* ijk,
                  uint32_t mask, double min_proba, void* work, float* proba, int32_t* label,
-                 uint8_t* known, cudaStream_t st) {
+                 uint8_t* known, cudaStream_t st, int cube_u8 = 0) {
   if (c->model.kind == 0) return fail(c, RML_E_NOMODEL, "rml_predict: no model loaded");
   if (feature_len(c, mask) != c->model.F)
     return fail(c, RML_E_INVALID, "rml_predict: mask gives F=%d but the model has F=%d",
@@ -423,9 +458,11 @@ int predict_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
   int32_t* norms = reinterpret_cast<int32_t*>(static_cast<char*>(work) + feat_bytes);
   // the scorer expects features scaled like common.process_samples(scale=True)
   const Affine aff{0.f, static_cast<float>(c->model.feature_scale), 1};
+  // uint8 cubes stream 4x faster, so the scorer gets a larger share of the SMs
+  const int k2_sms = cube_u8 ? c->k2_sms_u8 : c->k2_sms;
   const bool fused = c->fused_enabled && c->model.kind == 1 && dtype == RML_U8 && mode == RML_MODE_MAX &&
                      c->sx == kSX && c->sy == kSY && c->sz == kSZ && B >= c->fused_min_b &&
-                     c->k2_sms > 0 && c->k2_sms < c->num_sms;
+                     k2_sms > 0 && k2_sms < c->num_sms;
   c->last_fused = fused ? 1 : 0;
   if (fused) {
     // One pipeline, two co-resident kernels: K1 streams cubes on (num_sms - k2_sms) SMs and
@@ -449,11 +486,11 @@ int predict_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
     RML_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
     if (c->ev_k1a) RML_CUDA(c, cudaEventRecord(c->ev_k1a, st));
     int rc = project_impl(c, cubes, B, mode, ijk, mask, dtype, work, norms, st,
-                          c->num_sms - c->k2_sms, c->tile_done, &aff);
+                          c->num_sms - k2_sms, c->tile_done, &aff, cube_u8);
     if (c->ev_k1b) RML_CUDA(c, cudaEventRecord(c->ev_k1b, st));
     if (rc) return rc;
     rc = score_impl(c, work, dtype, norms, B, min_proba, proba, nullptr, label, known, c->aux_stream,
-                    c->k2_sms, c->tile_done);
+                    k2_sms, c->tile_done);
     if (rc) return rc;
     RML_CUDA(c, cudaEventRecord(c->ev_join, c->aux_stream));
     RML_CUDA(c, cudaStreamWaitEvent(st, c->ev_join, 0));
@@ -461,7 +498,7 @@ int predict_impl(rml_ctx* c, const float* cubes, int64_t B, int mode, const int3
     return RML_OK;
   }
   if (c->ev_k1a) RML_CUDA(c, cudaEventRecord(c->ev_k1a, st));
-  int rc = project_impl(c, cubes, B, mode, ijk, mask, dtype, work, norms, st, 0, nullptr, &aff);
+  int rc = project_impl(c, cubes, B, mode, ijk, mask, dtype, work, norms, st, 0, nullptr, &aff, cube_u8);
   if (c->ev_k1b) RML_CUDA(c, cudaEventRecord(c->ev_k1b, st));
   if (rc) return rc;
   rc = score_impl(c, work, dtype, norms, B, min_proba, proba, nullptr, label, known, st);
@@ -534,6 +571,8 @@ int rml_create(int device, rml_ctx** out) {
   // measured optimum on B200 (148 SMs): 32 scorer SMs, 116 projection SMs (profiles/r1_fused_sweep.txt)
   c->k2_sms = (c->num_sms * 32 + 74) / 148;
   if (const char* e1 = getenv("RML_K2_SMS")) c->k2_sms = atoi(e1);
+  c->k2_sms_u8 = (c->num_sms * 48 + 74) / 148;
+  if (const char* e4 = getenv("RML_K2_SMS_U8")) c->k2_sms_u8 = atoi(e4);
   if (const char* e2 = getenv("RML_FUSED")) c->fused_enabled = atoi(e2);
   if (const char* e3 = getenv("RML_FUSED_MIN_B")) c->fused_min_b = atoll(e3);
   *out = c;
@@ -729,6 +768,14 @@ int rml_project(rml_ctx* c, const float* cubes, int64_t B, int mode, const int32
   return project_impl(c, cubes, B, mode, ijk, mask, dtype, feats, norms, static_cast<cudaStream_t>(stream));
 }
 
+int rml_project_u8(rml_ctx* c, const uint8_t* cubes, int64_t B, int mode, const int32_t* ijk,
+                   uint32_t mask, int dtype, void* feats, int32_t* norms, rml_stream stream) {
+  if (!c) return RML_E_INVALID;
+  DeviceGuard g(c->device);
+  return project_impl(c, cubes, B, mode, ijk, mask, dtype, feats, norms, static_cast<cudaStream_t>(stream),
+                      0, nullptr, nullptr, 1);
+}
+
 int rml_process_samples(rml_ctx* c, const float* xz, const float* yz, const float* xy, int64_t B,
                         uint32_t mask, int scale, float* feats, rml_stream stream) {
   if (!c) return RML_E_INVALID;
@@ -814,9 +861,23 @@ int rml_predict(rml_ctx* c, const float* cubes, int64_t B, int mode, const int32
                       static_cast<cudaStream_t>(stream));
 }
 
-int rml_predict_host(rml_ctx* c, const float* cubes_host, int64_t B, int mode,
-                     const int32_t* ijk_host, uint32_t mask, double min_proba, float* proba_host,
-                     int32_t* label_host, uint8_t* known_host) {
+int rml_predict_u8(rml_ctx* c, const uint8_t* cubes, int64_t B, int mode, const int32_t* ijk,
+                   uint32_t mask, double min_proba, void* work, float* proba, int32_t* label,
+                   uint8_t* known, rml_stream stream) {
+  if (!c) return RML_E_INVALID;
+  DeviceGuard g(c->device);
+  return predict_impl(c, cubes, B, mode, ijk, mask, min_proba, work, proba, label, known,
+                      static_cast<cudaStream_t>(stream), 1);
+}
+
+}  // extern "C"
+
+namespace {
+// Host buffers in, host buffers out: the batch goes through the GPU in chunks on kHostBufs
+// streams so that the H2D copy of chunk n+1 overlaps the kernels and the D2H copy of chunk n.
+int predict_host_impl(rml_ctx* c, const void* cubes_host, int cube_u8, int64_t B, int mode,
+                      const int32_t* ijk_host, uint32_t mask, double min_proba, float* proba_host,
+                      int32_t* label_host, uint8_t* known_host) {
   if (!c) return RML_E_INVALID;
   if (c->model.kind == 0) return fail(c, RML_E_NOMODEL, "rml_predict_host: no model loaded");
   if (!cubes_host || !proba_host || !label_host || B < 0)
@@ -825,14 +886,16 @@ int rml_predict_host(rml_ctx* c, const float* cubes_host, int64_t B, int mode,
   if (B == 0) return RML_OK;
   DeviceGuard g(c->device);
   HostPipe& hp = c->pipe;
-  const int64_t chunk = 512;  // 512 cubes = 246 MB per H2D transfer
-  const size_t cube_elems = static_cast<size_t>(c->sx) * c->sy * c->sz;
+  // 512 float32 cubes = 246 MB per H2D transfer; uint8 cubes are a quarter of that, so twice the
+  // scans per chunk keeps the transfers long and the launches few
+  const int64_t chunk = cube_u8 ? 1024 : 512;
+  const size_t cube_bytes = static_cast<size_t>(c->sx) * c->sy * c->sz * (cube_u8 ? 1 : 4);
   const int C = c->model.C;
-  if (hp.chunk != chunk) {
+  if (hp.chunk != chunk || hp.cube_bytes != cube_bytes) {
     free_pipe(hp);
     hp.work_bytes = rml_predict_workspace_bytes(c, chunk);
     for (int i = 0; i < kHostBufs; ++i) {
-      RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.cubes[i]), chunk * cube_elems * 4));
+      RML_CUDA(c, cudaMalloc(&hp.cubes[i], chunk * cube_bytes));
       RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.ijk[i]), chunk * 3 * 4));
       RML_CUDA(c, cudaMalloc(&hp.work[i], hp.work_bytes));
       RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.proba[i]), chunk * kMaxClasses * 4));
@@ -841,18 +904,20 @@ int rml_predict_host(rml_ctx* c, const float* cubes_host, int64_t B, int mode,
       RML_CUDA(c, cudaStreamCreateWithFlags(&hp.stream[i], cudaStreamNonBlocking));
     }
     hp.chunk = chunk;
+    hp.cube_bytes = cube_bytes;
   }
+  const char* src = static_cast<const char*>(cubes_host);
   int64_t done = 0;
   int slot = 0;
   while (done < B) {
     const int64_t n = (B - done) < chunk ? (B - done) : chunk;
     cudaStream_t st = hp.stream[slot];
-    RML_CUDA(c, cudaMemcpyAsync(hp.cubes[slot], cubes_host + done * cube_elems, n * cube_elems * 4,
+    RML_CUDA(c, cudaMemcpyAsync(hp.cubes[slot], src + done * cube_bytes, n * cube_bytes,
                                 cudaMemcpyHostToDevice, st));
     if (mode == RML_MODE_SLICE)
       RML_CUDA(c, cudaMemcpyAsync(hp.ijk[slot], ijk_host + done * 3, n * 12, cudaMemcpyHostToDevice, st));
     int rc = predict_impl(c, hp.cubes[slot], n, mode, hp.ijk[slot], mask, min_proba, hp.work[slot],
-                          hp.proba[slot], hp.label[slot], hp.known[slot], st);
+                          hp.proba[slot], hp.label[slot], hp.known[slot], st, cube_u8);
     if (rc) return rc;
     RML_CUDA(c, cudaMemcpyAsync(proba_host + done * C, hp.proba[slot], n * C * 4, cudaMemcpyDeviceToHost, st));
     RML_CUDA(c, cudaMemcpyAsync(label_host + done, hp.label[slot], n * 4, cudaMemcpyDeviceToHost, st));
@@ -863,6 +928,23 @@ int rml_predict_host(rml_ctx* c, const float* cubes_host, int64_t B, int mode,
   }
   for (int i = 0; i < kHostBufs; ++i) RML_CUDA(c, cudaStreamSynchronize(hp.stream[i]));
   return RML_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rml_predict_host(rml_ctx* c, const float* cubes_host, int64_t B, int mode,
+                     const int32_t* ijk_host, uint32_t mask, double min_proba, float* proba_host,
+                     int32_t* label_host, uint8_t* known_host) {
+  return predict_host_impl(c, cubes_host, 0, B, mode, ijk_host, mask, min_proba, proba_host,
+                           label_host, known_host);
+}
+
+int rml_predict_host_u8(rml_ctx* c, const uint8_t* cubes_host, int64_t B, int mode,
+                        const int32_t* ijk_host, uint32_t mask, double min_proba, float* proba_host,
+                        int32_t* label_host, uint8_t* known_host) {
+  return predict_host_impl(c, cubes_host, 1, B, mode, ijk_host, mask, min_proba, proba_host,
+                           label_host, known_host);
 }
 
 int rml_check_status(rml_ctx* c, rml_stream stream) {
@@ -911,6 +993,13 @@ int rml_set_fused(rml_ctx* c, int enabled, int k2_sms, int64_t min_batch) {
   c->fused_enabled = enabled;
   if (k2_sms > 0) c->k2_sms = k2_sms;
   if (min_batch > 0) c->fused_min_b = min_batch;
+  return RML_OK;
+}
+
+int rml_set_fused_u8(rml_ctx* c, int k2_sms) {
+  if (!c) return RML_E_INVALID;
+  if (k2_sms <= 0 || k2_sms >= c->num_sms) return fail(c, RML_E_INVALID, "rml_set_fused_u8: k2_sms %d not in (0, %d)", k2_sms, c->num_sms);
+  c->k2_sms_u8 = k2_sms;
   return RML_OK;
 }
 
@@ -1381,9 +1470,9 @@ static int net_dense(rml_ctx* c, const uint16_t* flat, int64_t n_scans, float* p
 }
 
 // shared driver: conv towers chunk by chunk, dense stack once per dense group
-static int net_run(rml_ctx* c, const float* cubes, int mode, const int32_t* ijk, const float* feats,
+static int net_run(rml_ctx* c, const void* cubes, int mode, const int32_t* ijk, const float* feats,
                    const float* images, int64_t B, void* workspace, size_t workspace_bytes, float* proba,
-                   float* logits, int32_t* label, uint16_t* tower_bf16, cudaStream_t st) {
+                   float* logits, int32_t* label, uint16_t* tower_bf16, cudaStream_t st, int cube_u8 = 0) {
   NetPlan pl;
   int rc = net_make_plan(c, B, workspace_bytes, &pl);
   if (rc) return rc;
@@ -1405,8 +1494,9 @@ static int net_run(rml_ctx* c, const float* cubes, int mode, const int32_t* ijk,
       if (cubes) {
         // K1 with the network's scaling (p - 127.5) / 127.5 (dnn.py:202-205)
         const Affine aff{127.5f, 127.5f, 1};
-        rc = project_impl(c, cubes + s0 * cube_elems, n, mode, ijk ? ijk + s0 * 3 : nullptr, RML_MASK_ALL,
-                          RML_F32, feats_ws, nullptr, st, 0, nullptr, &aff);
+        const char* cube0 = static_cast<const char*>(cubes) + s0 * cube_elems * (cube_u8 ? 1 : 4);
+        rc = project_impl(c, cube0, n, mode, ijk ? ijk + s0 * 3 : nullptr, RML_MASK_ALL,
+                          RML_F32, feats_ws, nullptr, st, 0, nullptr, &aff, cube_u8);
         if (rc) return rc;
         f = feats_ws;
       } else if (feats) {
@@ -1471,6 +1561,18 @@ int rml_net_predict(rml_ctx* c, const float* cubes, int64_t B, int mode, const i
   DeviceGuard g(c->device);
   return net_run(c, cubes, mode, ijk, nullptr, nullptr, B, workspace, workspace_bytes, proba, nullptr, label,
                  nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int rml_net_predict_u8(rml_ctx* c, const uint8_t* cubes, int64_t B, int mode, const int32_t* ijk,
+                       void* workspace, size_t workspace_bytes, float* proba, int32_t* label,
+                       rml_stream stream) {
+  if (!c) return RML_E_INVALID;
+  if (!c->net.ready) return fail(c, RML_E_NOMODEL, "rml_net_predict_u8: no network loaded");
+  if (!cubes || !workspace || !proba || !label || B < 0) return fail(c, RML_E_INVALID, "rml_net_predict_u8: null buffer or B<0");
+  if (B == 0) return RML_OK;
+  DeviceGuard g(c->device);
+  return net_run(c, cubes, mode, ijk, nullptr, nullptr, B, workspace, workspace_bytes, proba, nullptr, label,
+                 nullptr, static_cast<cudaStream_t>(stream), 1);
 }
 
 }  // extern "C"

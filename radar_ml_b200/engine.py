@@ -121,17 +121,20 @@ class Engine:
     # ------------------------------------------------------------------ K1
     def _check_cubes(self, cubes):
         sx, sy, sz = self.dims
-        if not (isinstance(cubes, torch.Tensor) and cubes.is_cuda and cubes.dtype == torch.float32
+        if not (isinstance(cubes, torch.Tensor) and cubes.is_cuda
+                and cubes.dtype in (torch.float32, torch.uint8)
                 and cubes.is_contiguous() and cubes.dim() == 4
                 and tuple(cubes.shape[1:]) == (sx, sy, sz)):
-            raise ValueError("cubes must be a contiguous CUDA float32 tensor [B,%d,%d,%d]"
+            raise ValueError("cubes must be a contiguous CUDA float32 (or uint8) tensor [B,%d,%d,%d]"
                              % (sx, sy, sz))
         if cubes.device != self.device:
             raise ValueError("cubes are on %s, engine on %s" % (cubes.device, self.device))
+        return cubes.dtype == torch.uint8
 
     def project(self, cubes, mode="max", ijk=None, mask=MASK_ALL, dtype=F32, out=None, norms=None):
-        """cubes [B,sx,sy,sz] -> features [B,stride] (+ int32 norms for U8)."""
-        self._check_cubes(cubes)
+        """cubes [B,sx,sy,sz] (float32, or the sensor's integers as uint8) -> features
+        [B,stride] (+ int32 norms for U8)."""
+        cube_u8 = self._check_cubes(cubes)
         m = mask_bits(mask)
         B = cubes.shape[0]
         stride = self.feature_stride(m, dtype)
@@ -147,8 +150,9 @@ class Engine:
             ijk = ijk.to(device=self.device, dtype=torch.int32).contiguous()
         if B == 0:   # empty batch: nothing to launch (zero-size tensors have no storage)
             return (out, norms) if dtype == U8 else out
-        check(self.ctx, self.lib.rml_project(self.ctx, _ptr(cubes), B, md, _ptr(ijk), m, dtype,
-                                             _ptr(out), _ptr(norms), self._stream()))
+        fn = self.lib.rml_project_u8 if cube_u8 else self.lib.rml_project
+        check(self.ctx, fn(self.ctx, _ptr(cubes), B, md, _ptr(ijk), m, dtype, _ptr(out), _ptr(norms),
+                           self._stream()))
         return (out, norms) if dtype == U8 else out
 
     def process_samples(self, xz, yz, xy, mask=MASK_ALL, scale=False):
@@ -165,7 +169,8 @@ class Engine:
     def derive_targets(self, cubes, num_targets=1, want_sums=False):
         """common.py:45-80 on device: cubes [B,sx,sy,sz] -> ijk int32 [B,T,3] (ascending by sum;
         last = strongest) and optionally the float32 axis sums [B, sx+sy+sz]."""
-        self._check_cubes(cubes)
+        if self._check_cubes(cubes):
+            raise ValueError("derive_targets takes float32 cubes")
         B = cubes.shape[0]
         ijk = torch.empty((B, num_targets, 3), device=self.device, dtype=torch.int32)
         sums = torch.empty((B, sum(self.dims)), device=self.device, dtype=torch.float32) if want_sums else None
@@ -272,8 +277,9 @@ class Engine:
         return self._work
 
     def predict(self, cubes, mode="max", ijk=None, mask=MASK_ALL, min_proba=0.7, out=None):
-        """B scans -> (proba [B,C] f32, label [B] i32, known [B] u8) on the device, async."""
-        self._check_cubes(cubes)
+        """B scans (float32 or uint8 cubes) -> (proba [B,C] f32, label [B] i32, known [B] u8) on
+        the device, async."""
+        cube_u8 = self._check_cubes(cubes)
         if self.params is None:
             raise RadarMLError(_lib.E_NOMODEL, "no model loaded")
         B = cubes.shape[0]
@@ -292,18 +298,20 @@ class Engine:
         if B == 0:
             return proba, label, known
         work = self.workspace(B)
-        check(self.ctx, self.lib.rml_predict(self.ctx, _ptr(cubes), B, md, _ptr(ijk),
-                                             mask_bits(mask), float(min_proba), _ptr(work),
-                                             _ptr(proba), _ptr(label), _ptr(known), self._stream()))
+        fn = self.lib.rml_predict_u8 if cube_u8 else self.lib.rml_predict
+        check(self.ctx, fn(self.ctx, _ptr(cubes), B, md, _ptr(ijk), mask_bits(mask), float(min_proba),
+                           _ptr(work), _ptr(proba), _ptr(label), _ptr(known), self._stream()))
         return proba, label, known
 
     def predict_host(self, cubes: np.ndarray, mode="max", ijk=None, mask=MASK_ALL, min_proba=0.7,
                      out=None):
-        """Host float32 cubes [B,sx,sy,sz] in, host results out (H2D/compute/D2H overlapped)."""
+        """Host cubes [B,sx,sy,sz] (float32 as predict.py:91 makes them, or the sensor's integers
+        as uint8) in, host results out (H2D/compute/D2H overlapped)."""
         sx, sy, sz = self.dims
-        if not (isinstance(cubes, np.ndarray) and cubes.dtype == np.float32
+        if not (isinstance(cubes, np.ndarray) and cubes.dtype in (np.float32, np.uint8)
                 and cubes.flags.c_contiguous and cubes.shape[1:] == (sx, sy, sz)):
-            raise ValueError("cubes must be a C-contiguous float32 ndarray [B,%d,%d,%d]" % (sx, sy, sz))
+            raise ValueError("cubes must be a C-contiguous float32 (or uint8) ndarray [B,%d,%d,%d]"
+                             % (sx, sy, sz))
         if self.params is None:
             raise RadarMLError(_lib.E_NOMODEL, "no model loaded")
         B = cubes.shape[0]
@@ -320,8 +328,8 @@ class Engine:
             if ijk is None:
                 raise ValueError("slice mode needs ijk [B,3] int32")
             ij = np.ascontiguousarray(ijk, dtype=np.int32)
-        check(self.ctx, self.lib.rml_predict_host(self.ctx, _np_ptr(cubes), B, md, _np_ptr(ij),
-                                                  mask_bits(mask), float(min_proba), _np_ptr(proba),
-                                                  _np_ptr(label), _np_ptr(known)))
+        fn = self.lib.rml_predict_host_u8 if cubes.dtype == np.uint8 else self.lib.rml_predict_host
+        check(self.ctx, fn(self.ctx, _np_ptr(cubes), B, md, _np_ptr(ij), mask_bits(mask),
+                           float(min_proba), _np_ptr(proba), _np_ptr(label), _np_ptr(known)))
         self.check_status()
         return proba, label, known

@@ -220,10 +220,11 @@ class GpuNetClassifier:
         return res
 
     def predict_cubes(self, cubes, mode="max", ijk=None):
-        """cubes [B,22,31,176] CUDA -> (proba [B,C] f32, label [B] i32): K1 -> K3 -> K4 -> K5."""
+        """cubes [B,22,31,176] CUDA (float32 or uint8) -> (proba [B,C] f32, label [B] i32):
+        K1 -> K3 -> K4 -> K5."""
         import torch
         eng = self.engine
-        eng._check_cubes(cubes)
+        cube_u8 = eng._check_cubes(cubes)
         B = cubes.shape[0]
         Cn = self.spec.n_classes
         proba = torch.empty((B, Cn), device=eng.device, dtype=torch.float32)
@@ -236,7 +237,8 @@ class GpuNetClassifier:
                 raise ValueError("slice mode needs ijk [B,3] int32")
             ijk = ijk.to(device=eng.device, dtype=torch.int32).contiguous()
         ws = self._workspace()
-        check(eng.ctx, eng.lib.rml_net_predict(
+        fn = eng.lib.rml_net_predict_u8 if cube_u8 else eng.lib.rml_net_predict
+        check(eng.ctx, fn(
             eng.ctx, C.c_void_p(cubes.data_ptr()), B, md,
             C.c_void_p(ijk.data_ptr()) if ijk is not None else None, C.c_void_p(ws.data_ptr()),
             ws.numel(), C.c_void_p(proba.data_ptr()), C.c_void_p(label.data_ptr()), eng._stream()))
