@@ -238,7 +238,9 @@ int rml_check_status(rml_ctx* ctx, rml_stream stream); /* synchronises the strea
  * scorer is co-resident on the other k2_sms SMs and starts a tile the moment it is complete.
  * enabled=0 forces the serial K1 -> K2 order (also: env RML_FUSED=0, RML_K2_SMS, RML_FUSED_MIN_B). */
 int rml_set_fused(rml_ctx* ctx, int enabled, int k2_sms, int64_t min_batch);
-/* scorer SMs when the cubes are uint8 (they stream 4x faster; also env RML_K2_SMS_U8) */
+/* uint8 cubes: k2_sms > 0 selects the co-resident pipeline with that many scorer SMs, 0 (the
+ * default) the serial K1 -> K2 order — the byte-SIMD projection kernel is issue-bound and wants
+ * every SM, so serial measured faster (profiles/r1c_u8_sweep.txt).  Also env RML_K2_SMS_U8. */
 int rml_set_fused_u8(rml_ctx* ctx, int k2_sms);
 /* CUDA-event timing of the kernels inside the last rml_predict on this context: k1_ms =
  * projection kernel alone, total_ms = projection start -> scorer end.  Synchronises. */

@@ -23,7 +23,7 @@ namespace rml {
 constexpr int kSlabBytesU8 = kSlabElems;       // 5456
 constexpr int kU8Stages = 16;                  // 87 KB in flight per SM
 constexpr int kU8RowLanes = kSZ / 8;           // 22 lanes x uint2 per 176-byte row
-static_assert(kU8Stages % kColWarps == 0, "ring depth must be a multiple of the column-warp count");
+static_assert(kU8Stages % kColWarps == 0 && kU8Stages % 2 == 0 && kSX % 2 == 0, "ring depth must be a multiple of the column-warp count");
 static_assert(kSlabBytesU8 % 16 == 0 && kCubeElems % 16 == 0, "bulk copies need 16-byte granules");
 
 struct K1U8Params {
@@ -135,29 +135,51 @@ __device__ __forceinline__ void k1u8_row_warp(const K1U8Params& p, const unsigne
     const int buf = t & 1;
     OutT* stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
     mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
-    for (int i = 0; i < kSX; ++i, ++it) {
+    // two slabs per step (22 is even and the ring depth is even, so a pair never straddles a scan
+    // or the ring end): the running max takes both with one three-input maximum per register
+    for (int i = 0; i < kSX; i += 2, it += 2) {
       const int stage = it % kU8Stages;
-      mbar_wait(&full[stage], (it / kU8Stages) & 1);
+      const uint32_t ph = (it / kU8Stages) & 1;
+      mbar_wait(&full[stage], ph);
+      mbar_wait(&full[stage + 1], ph);
       const uint2* rows = reinterpret_cast<const uint2*>(slabs + stage * kSlabBytesU8 + j0 * kSZ);
-      uint2 v[NR];
-#pragma unroll
-      for (int r = 0; r < NR; ++r) v[r] = act ? rows[r * kU8RowLanes + lane] : make_uint2(0u, 0u);
-      uint32_t m[NR];
+      constexpr int kNext = kSlabBytesU8 / 8;      // uint2 per slab
+      uint2 va[NR], vb[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
-        const U16x8 u = unpack_u8x8(v[r]);
-        max_u16x8(yz[r], u);
-        m[r] = hmax_u16x8(u);
+        va[r] = act ? rows[r * kU8RowLanes + lane] : make_uint2(0u, 0u);
+        vb[r] = act ? rows[kNext + r * kU8RowLanes + lane] : make_uint2(0u, 0u);
+      }
+      uint32_t ma[NR], mb[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const U16x8 ua = unpack_u8x8(va[r]);
+        const U16x8 ub = unpack_u8x8(vb[r]);
+        max3_u16x8(yz[r], ua, ub);
+        ma[r] = hmax_u16x8(ua);
+        mb[r] = hmax_u16x8(ub);
       }
 #pragma unroll
-      for (int r = 0; r < NR; ++r) m[r] = __reduce_max_sync(0xffffffffu, m[r]);
+      for (int r = 0; r < NR; ++r) {
+        ma[r] = __reduce_max_sync(0xffffffffu, ma[r]);
+        mb[r] = __reduce_max_sync(0xffffffffu, mb[r]);
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stage]);    // the slab has been consumed
-      uint32_t mine = m[0];
+      if (lane == 0) {                               // both slabs have been consumed
+        mbar_arrive(&empty[stage]);
+        mbar_arrive(&empty[stage + 1]);
+      }
+      // lanes 0..NR-1 store the xy values of slab i, lanes NR..2NR-1 those of slab i+1
+      uint32_t mine = 0;
 #pragma unroll
-      for (int r = 1; r < NR; ++r) mine = (lane == r) ? m[r] : mine;
-      if (lane < NR && (p.mask & 4u))
-        EmitB<OutT>::put1(stg, off_xy + i * kSY + j0 + lane, mine, p, sumsq);
+      for (int r = 0; r < NR; ++r) {
+        mine = (lane == r) ? ma[r] : mine;
+        mine = (lane == NR + r) ? mb[r] : mine;
+      }
+      if (lane < 2 * NR && (p.mask & 4u)) {
+        const int second = lane >= NR ? 1 : 0;
+        EmitB<OutT>::put1(stg, off_xy + (i + second) * kSY + j0 + lane - second * NR, mine, p, sumsq);
+      }
     }
     // end of scan: the running max over i is the yz projection
 #pragma unroll
@@ -177,8 +199,14 @@ __device__ __forceinline__ void k1u8_row_warp(const K1U8Params& p, const unsigne
   }
 }
 
+// u8 rows: 108 KB of shared memory and 48 registers per thread, so two CTAs share an SM — the
+// kernel is issue-bound (no byte-wise max instruction), and the second CTA fills the issue slots
+// the first leaves idle while it waits on barriers.  f32 rows (167 KB) run one CTA per SM.
 template <typename OutT>
-__global__ void __launch_bounds__(kK1Threads, 1) k1_project_max_u8in(const K1U8Params p) {
+__host__ __device__ constexpr int k1u8_ctas_per_sm() { return sizeof(OutT) == 1 ? 2 : 1; }
+
+template <typename OutT>
+__global__ void __launch_bounds__(kK1Threads, k1u8_ctas_per_sm<OutT>()) k1_project_max_u8in(const K1U8Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* slabs = smem;
   OutT* stg0 = reinterpret_cast<OutT*>(smem + kU8Stages * kSlabBytesU8);

@@ -116,7 +116,11 @@ struct rml_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_k1a = nullptr, ev_k1b = nullptr, ev_k2b = nullptr;
   unsigned int* tile_done = nullptr;
   int64_t tile_done_cap = 0;
-  int k2_sms_u8 = 48;        // same for uint8 cubes (RML_K2_SMS_U8)
+  // uint8 cubes: the projection kernel is issue-bound, not HBM-bound, so it wants every SM (two
+  // CTAs each) and the serial K1 -> K2 order wins (profiles/r1c_u8_sweep.txt); k2_sms_u8 > 0
+  // (rml_set_fused_u8 / RML_K2_SMS_U8) still selects the co-resident pipeline
+  int k2_sms_u8 = 0;
+  int k1u8_ctas_per_sm = 2;  // RML_K1U8_CTAS
   int k2_sms = 32;           // SMs reserved for the scorer in fused mode (RML_K2_SMS); set from the SM count in rml_create
   int64_t fused_min_b = 8192;
   int fused_enabled = 1;     // RML_FUSED=0 disables
@@ -300,7 +304,9 @@ int project_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32
     p.offset = aff.offset; p.scale = aff.scale; p.affine = aff.enabled;
     p.tile_done = dtype == RML_U8 ? tile_done : nullptr;
     const int sms = grid_limit > 0 ? grid_limit : c->num_sms;
-    const int grid = static_cast<int>(B < sms ? B : sms);
+    const int64_t ctas = static_cast<int64_t>(sms) *
+                         (dtype == RML_U8 && grid_limit <= 0 ? c->k1u8_ctas_per_sm : 1);
+    const int grid = static_cast<int>(B < ctas ? B : ctas);
     if (dtype == RML_U8) {
       const int smem = k1u8_smem_bytes<uint8_t>();
       RML_CUDA(c, cudaFuncSetAttribute(k1_project_max_u8in<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -571,8 +577,8 @@ int rml_create(int device, rml_ctx** out) {
   // measured optimum on B200 (148 SMs): 32 scorer SMs, 116 projection SMs (profiles/r1_fused_sweep.txt)
   c->k2_sms = (c->num_sms * 32 + 74) / 148;
   if (const char* e1 = getenv("RML_K2_SMS")) c->k2_sms = atoi(e1);
-  c->k2_sms_u8 = (c->num_sms * 48 + 74) / 148;
   if (const char* e4 = getenv("RML_K2_SMS_U8")) c->k2_sms_u8 = atoi(e4);
+  if (const char* e5 = getenv("RML_K1U8_CTAS")) { const int v = atoi(e5); if (v == 1 || v == 2) c->k1u8_ctas_per_sm = v; }
   if (const char* e2 = getenv("RML_FUSED")) c->fused_enabled = atoi(e2);
   if (const char* e3 = getenv("RML_FUSED_MIN_B")) c->fused_min_b = atoll(e3);
   *out = c;
@@ -998,7 +1004,7 @@ int rml_set_fused(rml_ctx* c, int enabled, int k2_sms, int64_t min_batch) {
 
 int rml_set_fused_u8(rml_ctx* c, int k2_sms) {
   if (!c) return RML_E_INVALID;
-  if (k2_sms <= 0 || k2_sms >= c->num_sms) return fail(c, RML_E_INVALID, "rml_set_fused_u8: k2_sms %d not in (0, %d)", k2_sms, c->num_sms);
+  if (k2_sms < 0 || k2_sms >= c->num_sms) return fail(c, RML_E_INVALID, "rml_set_fused_u8: k2_sms %d not in [0, %d)", k2_sms, c->num_sms);
   c->k2_sms_u8 = k2_sms;
   return RML_OK;
 }

@@ -32,7 +32,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scans", type=int, default=65536)
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--splits", default="24,32,48,64,80,96")
+    ap.add_argument("--splits", default="24,48")
     ap.add_argument("--only-default", action="store_true", help="profiling aid: one configuration")
     args = ap.parse_args()
     B = args.scans
@@ -60,7 +60,7 @@ def main():
         eng.check_status()
         ok = all(torch.equal(a, b) for a, b in zip(out, ref))
         rows.append({"k2_sms": sms, "ms": ms, "scans_per_s": B / ms * 1e3, "identical": ok})
-    eng.lib.rml_set_fused(eng.ctx, 0, 0, 0)
+    assert eng.lib.rml_set_fused_u8(eng.ctx, 0) == 0
     eng.predict(cubes8, out=out)
     ms = timed(lambda: eng.predict(cubes8, out=out), args.steps)
     rows.append({"k2_sms": "serial", "ms": ms, "scans_per_s": B / ms * 1e3,
