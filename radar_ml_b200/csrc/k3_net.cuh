@@ -260,14 +260,27 @@ struct ResizeConv1Params {
   float alpha;
 };
 
+// Shared-memory layout (floats): projection [H][W] | horizontal pass [H][R] | image with a zero
+// border [(R+2)][R+16], each region rounded up to 16 bytes.  The border makes every 3x3 tap of the
+// first layer an unconditional load (TF 'same' padding is just the zeros around the image), and
+// with pad_l == 0 the 9 taps of a row of four output pixels are two 16-byte loads and one scalar.
+__host__ __device__ constexpr int k34_round4(int v) { return (v + 3) & ~3; }
+__host__ __device__ constexpr int k34_pitch(int R) { return R + 16; }
+__host__ __device__ constexpr int k34_smem_floats(int H, int W, int R) {
+  return k34_round4(H * W) + k34_round4(H * R) + (R + 2) * k34_pitch(R);
+}
+
 template <int CPL>
 __global__ void __launch_bounds__(256) k34_resize_conv1(const ResizeConv1Params p) {
-  extern __shared__ float rc_smem[];
+  extern __shared__ __align__(16) float rc_smem[];
   const int br = blockIdx.y;
   const int H = p.rz.ph[br], W = p.rz.pw[br], R = p.rz.R;
-  float* src = rc_smem;               // [H][W]
-  float* tmp = src + H * W;           // [H][R]
-  float* img = tmp + H * R;           // [R][R]
+  const int P = k34_pitch(R);
+  float* src = rc_smem;                           // [H][W]
+  float* tmp = src + k34_round4(H * W);           // [H][R]
+  float* img = tmp + k34_round4(H * R);           // [(R+2)][P], interior at (pad_t, colpad)
+  const int colpad = p.pad_l ? 4 : 0;
+  const int coff = colpad - p.pad_l;              // column of tap ix = -pad_l
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   float w[9][CPL], bs[CPL];
 #pragma unroll
@@ -281,6 +294,8 @@ __global__ void __launch_bounds__(256) k34_resize_conv1(const ResizeConv1Params 
   const int2* bh = p.rz.bh[br];
   const int2* bv = p.rz.bv[br];
   const int ksh = p.rz.ksh[br], ksv = p.rz.ksv[br];
+  for (int e = threadIdx.x; e < (R + 2) * P; e += blockDim.x) img[e] = 0.f;   // the border stays zero
+  __syncthreads();
   for (int64_t b = blockIdx.x; b < p.rz.B; b += gridDim.x) {
     const float* g = p.rz.feats + b * p.rz.F + p.rz.poff[br];
     for (int e = threadIdx.x; e < H * W; e += blockDim.x) src[e] = g[e];
@@ -298,25 +313,31 @@ __global__ void __launch_bounds__(256) k34_resize_conv1(const ResizeConv1Params 
       const int2 bd = bv[yy];
       double ss = 0.0;
       for (int y = 0; y < bd.y; ++y) ss += static_cast<double>(tmp[(bd.x + y) * R + xx]) * kv[yy * ksv + y];
-      img[e] = static_cast<float>(ss);
+      img[(yy + p.pad_t) * P + xx + colpad] = static_cast<float>(ss);
     }
     __syncthreads();
     // first tower layer straight from the smem image: a warp per output row, a lane per CPL channels
     __nv_bfloat16* out = p.out + (b * 3 + br) * static_cast<int64_t>(p.Ho) * p.Wo * p.Cout + lane * CPL;
     for (int oy = warp; oy < p.Ho; oy += nw) {
-      const int iy0 = oy * 2 - p.pad_t;
+      const float* row0 = img + (2 * oy) * P + coff;      // tap (kh = 0, ix = -pad_l) of pixel ox = 0
+      __nv_bfloat16* orow = out + static_cast<int64_t>(oy) * p.Wo * p.Cout;
       for (int ox0 = 0; ox0 < p.Wo; ox0 += 4) {
-        const int ix0 = ox0 * 2 - p.pad_l;
         float x[3][9];
+        if (coff == 0) {
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const int iy = iy0 + r;
-          const bool rowok = iy >= 0 && iy < R;
-#pragma unroll
-          for (int cx = 0; cx < 9; ++cx) {
-            const int ix = ix0 + cx;
-            x[r][cx] = (rowok && ix >= 0 && ix < R) ? img[iy * R + ix] : 0.f;
+          for (int r = 0; r < 3; ++r) {
+            const float* q = row0 + r * P + 2 * ox0;      // 32-byte aligned
+            const float4 a = *reinterpret_cast<const float4*>(q);
+            const float4 c4 = *reinterpret_cast<const float4*>(q + 4);
+            x[r][0] = a.x; x[r][1] = a.y; x[r][2] = a.z; x[r][3] = a.w;
+            x[r][4] = c4.x; x[r][5] = c4.y; x[r][6] = c4.z; x[r][7] = c4.w;
+            x[r][8] = q[8];
           }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cx = 0; cx < 9; ++cx) x[r][cx] = row0[r * P + 2 * ox0 + cx];
         }
 #pragma unroll
         for (int px = 0; px < 4; ++px) {
@@ -330,11 +351,16 @@ __global__ void __launch_bounds__(256) k34_resize_conv1(const ResizeConv1Params 
               for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) acc[c] = fmaf(x[r][2 * px + kw], w[r * 3 + kw][c], acc[c]);
-            __nv_bfloat16* o = out + (static_cast<int64_t>(oy) * p.Wo + ox0 + px) * p.Cout;
+            uint32_t pk[CPL / 2];
 #pragma unroll
-            for (int c = 0; c < CPL; c += 2)
-              *reinterpret_cast<__nv_bfloat162*>(o + c) =
+            for (int c = 0; c < CPL; c += 2) {
+              const __nv_bfloat162 h2 =
                   __floats2bfloat162_rn(apply_act(acc[c], p.act, p.alpha), apply_act(acc[c + 1], p.act, p.alpha));
+              pk[c >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            __nv_bfloat16* o = orow + static_cast<int64_t>(ox0 + px) * p.Cout;
+            if (CPL == 4) *reinterpret_cast<uint2*>(o) = make_uint2(pk[0], pk[CPL / 2 - 1]);
+            else *reinterpret_cast<uint32_t*>(o) = pk[0];
           }
         }
       }
@@ -354,8 +380,10 @@ __global__ void __launch_bounds__(256) k34_resize_conv1(const ResizeConv1Params 
 // bf16 come through a 2-D map.  Same warp roles as k5_dense_stack; the epilogue adds the bias,
 // applies ReLU / LeakyReLU and writes NHWC bf16.
 constexpr int kCgThreads = 192;
-constexpr int kCgStages = 6;
+constexpr int kCgMaxStages = 12;
 struct ConvGemmParams {
+  int stages;             // TMA ring depth: as many (A tile + weight tile) stages as fit, the loop is
+                          // bound by load latency (one 128-byte pixel row per TMA element)
   int64_t n_img;
   int Ho, Wo, Cin, Cout;
   int TH;                 // output rows per tile (TH * Wo <= 128)
@@ -367,8 +395,11 @@ struct ConvGemmParams {
   __nv_bfloat16* out;     // [n_img][Ho][Wo][Cout]
 };
 __host__ __device__ constexpr int cg_stage_bytes(int cout) { return 128 * 128 + cout * 128; }
-__host__ __device__ constexpr int cg_smem_bytes(int cout) {
-  return kCgStages * cg_stage_bytes(cout) + 1024 + 256 + 3 * 128 * 4;
+__host__ __device__ constexpr int cg_pick_stages(int cout) {
+  return 204800 / cg_stage_bytes(cout) < kCgMaxStages ? 204800 / cg_stage_bytes(cout) : kCgMaxStages;
+}
+__host__ __device__ constexpr int cg_smem_bytes(int cout, int stages) {
+  return stages * cg_stage_bytes(cout) + 1024 + 256 + 3 * 128 * 4;
 }
 
 __global__ void __launch_bounds__(kCgThreads, 1)
@@ -378,13 +409,14 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int stage_bytes = cg_stage_bytes(p.Cout);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCgStages * stage_bytes);
+  const int n_stages = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * stage_bytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kCgStages;
-  uint64_t* tfull = empty + kCgStages;
+  uint64_t* empty = bars + n_stages;
+  uint64_t* tfull = empty + n_stages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_bias = reinterpret_cast<float*>(smem + kCgStages * stage_bytes + 256);   // [3][Cout<=128]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);     // (2 * 12 + 4) * 8 + 4 <= 256
+  float* s_bias = reinterpret_cast<float*>(smem + n_stages * stage_bytes + 256);   // [3][Cout<=128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -395,7 +427,7 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 
   for (int e = threadIdx.x; e < 3 * p.Cout; e += blockDim.x) s_bias[e] = p.bias[e];
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kCgStages; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -427,8 +459,8 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         for (int tap = 0; tap < 9; ++tap) {
           const int kh = tap / 3, kw = tap - kh * 3;
           for (int cb = 0; cb < cblocks; ++cb, ++kit) {
-            const int s = kit % kCgStages;
-            mbar_wait(&empty[s], ((kit / kCgStages) & 1) ^ 1);
+            const int s = kit % n_stages;
+            mbar_wait(&empty[s], ((kit / n_stages) & 1) ^ 1);
             unsigned char* a_dst = smem + s * stage_bytes;
             unsigned char* b_dst = a_dst + 128 * 128;
             mbar_arrive_expect_tx(&full[s], a_bytes + p.Cout * 128);
@@ -449,8 +481,8 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * 128;
         for (int kb = 0; kb < k_blocks; ++kb, ++kit) {
-          const int s = kit % kCgStages;
-          mbar_wait(&full[s], (kit / kCgStages) & 1);
+          const int s = kit % n_stages;
+          mbar_wait(&full[s], (kit / n_stages) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           const uint32_t b_addr = a_addr + 128 * 128;

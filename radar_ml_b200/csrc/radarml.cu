@@ -1363,7 +1363,7 @@ static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_
       fp.rz.kh[b] = n.kh[b]; fp.rz.kv[b] = n.kv[b]; fp.rz.bh[b] = n.bh[b]; fp.rz.bv[b] = n.bv[b];
       fp.rz.ksh[b] = n.ksh[b]; fp.rz.ksv[b] = n.ksv[b];
       fp.w[b] = cv.w[b]; fp.bias[b] = cv.bias[b];
-      const int sm = (ph[b] * pw[b] + ph[b] * n.R + n.R * n.R) * 4;
+      const int sm = k34_smem_floats(ph[b], pw[b], n.R) * 4;
       if (sm > smem_max) smem_max = sm;
     }
     const int ho = (hw + 1) / 2;
@@ -1412,7 +1412,8 @@ static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_
       gp.tiles_per_img = (ho + th - 1) / th; gp.pad_t = pad; gp.pad_l = pad;
       gp.act = cv.act; gp.alpha = n.alpha; gp.bias = cv.bias3;
       gp.out = reinterpret_cast<__nv_bfloat16*>(dst);
-      const int smem = cg_smem_bytes(cv.cout);
+      gp.stages = cg_pick_stages(cv.cout);
+      const int smem = cg_smem_bytes(cv.cout, gp.stages);
       RML_CUDA(c, cudaFuncSetAttribute(k4_conv_igemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       const int64_t tiles = gp.n_img * gp.tiles_per_img;
       const int grid = static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
