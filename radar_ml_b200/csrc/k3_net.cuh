@@ -34,6 +34,89 @@ struct ResizeParams {
   int ksh[3], ksv[3];
 };
 
+// The two passes of Pillow's ImagingResample for one image held in shared memory, by one CTA.
+// Arithmetic is Pillow's: for each output, ss = 0.0; ss += (double)in[xmin + x] * k[x] for x in
+// [0, xmax) in that order; store (float)ss — what keeps the result bit-identical to PIL.
+// Mapping: a thread owns one output column and walks over rows, so the horizontal coefficients
+// of its column sit in registers (no per-tap coefficient load, no index division) and the
+// vertical coefficients of a row are warp-uniform loads.  The tap loop is unrolled to 5, 8 or 12
+// slots (5 taps when enlarging, 7 for 176 -> 128, 11 for 176 -> 80): a predicated-off slot still
+// issues, so the unroll follows the table; longer tables take the plain loop.
+constexpr int kResizeTaps = 12;
+
+template <int KT>
+__device__ __forceinline__ void resize_rows_h(const float* src, float* tmp, int H, int W, int R,
+                                              const double* kh, const int2* bh, int ksh) {
+  const int groups = blockDim.x / R;
+  const int xx = threadIdx.x % R, grp = threadIdx.x / R;
+  if (grp >= groups) return;
+  const int2 bd = bh[xx];
+  double k[KT];
+#pragma unroll
+  for (int x = 0; x < KT; ++x) k[x] = x < bd.y ? kh[xx * ksh + x] : 0.0;
+  for (int y = grp; y < H; y += groups) {
+    const float* in = src + y * W + bd.x;
+    double ss = 0.0;
+#pragma unroll
+    for (int x = 0; x < KT; ++x)
+      if (x < bd.y) ss += static_cast<double>(in[x]) * k[x];
+    tmp[y * R + xx] = static_cast<float>(ss);
+  }
+}
+
+template <int KT>
+__device__ __forceinline__ void resize_rows_v(const float* tmp, float* out, int out_pitch, int R,
+                                              const double* kv, const int2* bv, int ksv) {
+  const int groups = blockDim.x / R;
+  const int xx = threadIdx.x % R, grp = threadIdx.x / R;
+  if (grp >= groups) return;
+  for (int yy = grp; yy < R; yy += groups) {
+    const int2 bd = bv[yy];
+    const float* in = tmp + bd.x * R + xx;
+    const double* k = kv + yy * ksv;
+    double ss = 0.0;
+#pragma unroll
+    for (int y = 0; y < KT; ++y)
+      if (y < bd.y) ss += static_cast<double>(in[y * R]) * k[y];
+    out[yy * out_pitch + xx] = static_cast<float>(ss);
+  }
+}
+
+__device__ __forceinline__ void resize_pass_h(const float* src, float* tmp, int H, int W, int R,
+                                              const double* kh, const int2* bh, int ksh) {
+  if (ksh <= kResizeTaps && R <= static_cast<int>(blockDim.x)) {
+    if (ksh <= 5) resize_rows_h<5>(src, tmp, H, W, R, kh, bh, ksh);
+    else if (ksh <= 8) resize_rows_h<8>(src, tmp, H, W, R, kh, bh, ksh);
+    else resize_rows_h<kResizeTaps>(src, tmp, H, W, R, kh, bh, ksh);
+  } else {
+    for (int e = threadIdx.x; e < H * R; e += blockDim.x) {
+      const int y = e / R, xx = e - y * R;
+      const int2 bd = bh[xx];
+      double ss = 0.0;
+      for (int x = 0; x < bd.y; ++x) ss += static_cast<double>(src[y * W + bd.x + x]) * kh[xx * ksh + x];
+      tmp[e] = static_cast<float>(ss);
+    }
+  }
+}
+
+// out[yy * out_pitch + xx] for yy, xx < R (out may be shared or global memory)
+__device__ __forceinline__ void resize_pass_v(const float* tmp, float* out, int out_pitch, int R,
+                                              const double* kv, const int2* bv, int ksv) {
+  if (ksv <= kResizeTaps && R <= static_cast<int>(blockDim.x)) {
+    if (ksv <= 5) resize_rows_v<5>(tmp, out, out_pitch, R, kv, bv, ksv);
+    else if (ksv <= 8) resize_rows_v<8>(tmp, out, out_pitch, R, kv, bv, ksv);
+    else resize_rows_v<kResizeTaps>(tmp, out, out_pitch, R, kv, bv, ksv);
+  } else {
+    for (int e = threadIdx.x; e < R * R; e += blockDim.x) {
+      const int yy = e / R, xx = e - yy * R;
+      const int2 bd = bv[yy];
+      double ss = 0.0;
+      for (int y = 0; y < bd.y; ++y) ss += static_cast<double>(tmp[(bd.x + y) * R + xx]) * kv[yy * ksv + y];
+      out[yy * out_pitch + xx] = static_cast<float>(ss);
+    }
+  }
+}
+
 // one CTA per (scan, branch); smem: projection + horizontal-pass result
 __global__ void __launch_bounds__(256) k3_resize_pil(const ResizeParams p) {
   extern __shared__ float rs_smem[];
@@ -45,29 +128,11 @@ __global__ void __launch_bounds__(256) k3_resize_pil(const ResizeParams p) {
     const float* g = p.feats + b * p.F + p.poff[br];
     for (int e = threadIdx.x; e < H * W; e += blockDim.x) src[e] = g[e];
     __syncthreads();
-    // horizontal pass (ImagingResampleHorizontal_32bpc): double accumulate, float store
-    const double* kh = p.kh[br];
-    const int2* bh = p.bh[br];
-    const int ksh = p.ksh[br];
-    for (int e = threadIdx.x; e < H * R; e += blockDim.x) {
-      const int y = e / R, xx = e - y * R;
-      const int2 bd = bh[xx];
-      double ss = 0.0;
-      for (int x = 0; x < bd.y; ++x) ss += static_cast<double>(src[y * W + bd.x + x]) * kh[xx * ksh + x];
-      tmp[e] = static_cast<float>(ss);
-    }
+    // horizontal pass (ImagingResampleHorizontal_32bpc), then vertical: double accumulate, float store
+    resize_pass_h(src, tmp, H, W, R, p.kh[br], p.bh[br], p.ksh[br]);
     __syncthreads();
-    const double* kv = p.kv[br];
-    const int2* bv = p.bv[br];
-    const int ksv = p.ksv[br];
-    float* out = p.images + (b * 3 + br) * static_cast<int64_t>(R) * R;
-    for (int e = threadIdx.x; e < R * R; e += blockDim.x) {
-      const int yy = e / R, xx = e - yy * R;
-      const int2 bd = bv[yy];
-      double ss = 0.0;
-      for (int y = 0; y < bd.y; ++y) ss += static_cast<double>(tmp[(bd.x + y) * R + xx]) * kv[yy * ksv + y];
-      out[e] = static_cast<float>(ss);
-    }
+    resize_pass_v(tmp, p.images + (b * 3 + br) * static_cast<int64_t>(R) * R, R, R, p.kv[br], p.bv[br],
+                  p.ksv[br]);
     __syncthreads();
   }
 }
@@ -300,21 +365,9 @@ __global__ void __launch_bounds__(256) k34_resize_conv1(const ResizeConv1Params 
     const float* g = p.rz.feats + b * p.rz.F + p.rz.poff[br];
     for (int e = threadIdx.x; e < H * W; e += blockDim.x) src[e] = g[e];
     __syncthreads();
-    for (int e = threadIdx.x; e < H * R; e += blockDim.x) {
-      const int y = e / R, xx = e - y * R;
-      const int2 bd = bh[xx];
-      double ss = 0.0;
-      for (int x = 0; x < bd.y; ++x) ss += static_cast<double>(src[y * W + bd.x + x]) * kh[xx * ksh + x];
-      tmp[e] = static_cast<float>(ss);
-    }
+    resize_pass_h(src, tmp, H, W, R, kh, bh, ksh);
     __syncthreads();
-    for (int e = threadIdx.x; e < R * R; e += blockDim.x) {
-      const int yy = e / R, xx = e - yy * R;
-      const int2 bd = bv[yy];
-      double ss = 0.0;
-      for (int y = 0; y < bd.y; ++y) ss += static_cast<double>(tmp[(bd.x + y) * R + xx]) * kv[yy * ksv + y];
-      img[(yy + p.pad_t) * P + xx + colpad] = static_cast<float>(ss);
-    }
+    resize_pass_v(tmp, img + p.pad_t * P + colpad, P, R, kv, bv, ksv);
     __syncthreads();
     // first tower layer straight from the smem image: a warp per output row, a lane per CPL channels
     __nv_bfloat16* out = p.out + (b * 3 + br) * static_cast<int64_t>(p.Ho) * p.Wo * p.Cout + lane * CPL;
