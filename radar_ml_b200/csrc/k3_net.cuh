@@ -434,9 +434,13 @@ __global__ void __launch_bounds__(256) k34_resize_conv1(const ResizeConv1Params 
 // applies ReLU / LeakyReLU and writes NHWC bf16.
 constexpr int kCgThreads = 192;
 constexpr int kCgMaxStages = 12;
+// A ring stage holds the THREE taps of one kernel row (kw = 0,1,2) of one 64-channel block: three A
+// tiles + three weight tiles, 12 UMMAs, ONE full/empty barrier round trip.  Measured (profiles/
+// r1c_nets_experiments.txt): with one tap per stage the barrier protocol alone — no TMA, no MMA —
+// cost 650 cycles per stage, 70 % of the kernel; the tensor floor of a stage is 64-128 cycles.
+constexpr int kCgTapsPerStage = 3;
 struct ConvGemmParams {
-  int stages;             // TMA ring depth: as many (A tile + weight tile) stages as fit, the loop is
-                          // bound by load latency (one 128-byte pixel row per TMA element)
+  int stages;             // TMA ring depth (as many stages as fit)
   int64_t n_img;
   int Ho, Wo, Cin, Cout;
   int TH;                 // output rows per tile (TH * Wo <= 128)
@@ -447,9 +451,11 @@ struct ConvGemmParams {
   const float* bias;      // [3][Cout]
   __nv_bfloat16* out;     // [n_img][Ho][Wo][Cout]
 };
-__host__ __device__ constexpr int cg_stage_bytes(int cout) { return 128 * 128 + cout * 128; }
+__host__ __device__ constexpr int cg_stage_bytes(int cout) { return kCgTapsPerStage * (128 * 128 + cout * 128); }
 __host__ __device__ constexpr int cg_pick_stages(int cout) {
-  return 204800 / cg_stage_bytes(cout) < kCgMaxStages ? 204800 / cg_stage_bytes(cout) : kCgMaxStages;
+  return (232448 - 1024 - 256 - 3 * 128 * 4) / cg_stage_bytes(cout) < kCgMaxStages
+             ? (232448 - 1024 - 256 - 3 * 128 * 4) / cg_stage_bytes(cout)
+             : kCgMaxStages;
 }
 __host__ __device__ constexpr int cg_smem_bytes(int cout, int stages) {
   return stages * cg_stage_bytes(cout) + 1024 + 256 + 3 * 128 * 4;
@@ -475,8 +481,9 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int64_t n_tiles = p.n_img * p.tiles_per_img;
   const int cblocks = p.Cin / 64;
-  const int k_blocks = 9 * cblocks;
+  const int k_stages = 3 * cblocks;                 // ring stages per tile: (kernel row, channel block)
   const int a_bytes = p.TH * p.Wo * 128;
+  const int w_tile = p.Cout * 128;
 
   for (int e = threadIdx.x; e < 3 * p.Cout; e += blockDim.x) s_bias[e] = p.bias[e];
   if (threadIdx.x == 0) {
@@ -509,17 +516,20 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         int oy0 = tb * p.TH;
         if (oy0 > p.Ho - p.TH) oy0 = p.Ho - p.TH;        // last block overlaps instead of being ragged
         const int br = static_cast<int>(img % 3);
-        for (int tap = 0; tap < 9; ++tap) {
-          const int kh = tap / 3, kw = tap - kh * 3;
+        for (int kh = 0; kh < 3; ++kh) {
           for (int cb = 0; cb < cblocks; ++cb, ++kit) {
             const int s = kit % n_stages;
             mbar_wait(&empty[s], ((kit / n_stages) & 1) ^ 1);
             unsigned char* a_dst = smem + s * stage_bytes;
-            unsigned char* b_dst = a_dst + 128 * 128;
-            mbar_arrive_expect_tx(&full[s], a_bytes + p.Cout * 128);
-            tma_load_4d(a_dst, &map_x, cb * 64, kw - p.pad_l, 2 * oy0 + kh - p.pad_t,
-                        static_cast<int32_t>(img), &full[s], pol_a);
-            tma_load_2d(b_dst, &map_w, (tap * cblocks + cb) * 64, br * p.Cout, &full[s], pol_b);
+            unsigned char* b_dst = a_dst + kCgTapsPerStage * 128 * 128;
+            mbar_arrive_expect_tx(&full[s], kCgTapsPerStage * (a_bytes + w_tile));
+#pragma unroll
+            for (int kw = 0; kw < kCgTapsPerStage; ++kw) {
+              tma_load_4d(a_dst + kw * 128 * 128, &map_x, cb * 64, kw - p.pad_l, 2 * oy0 + kh - p.pad_t,
+                          static_cast<int32_t>(img), &full[s], pol_a);
+              tma_load_2d(b_dst + kw * w_tile, &map_w, ((kh * 3 + kw) * cblocks + cb) * 64, br * p.Cout,
+                          &full[s], pol_b);
+            }
           }
         }
       }
@@ -533,17 +543,20 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         mbar_wait(&tempty[ab], ((ait >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * 128;
-        for (int kb = 0; kb < k_blocks; ++kb, ++kit) {
+        for (int kb = 0; kb < k_stages; ++kb, ++kit) {
           const int s = kit % n_stages;
           mbar_wait(&full[s], (kit / n_stages) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint32_t b_addr = a_addr + 128 * 128;
-          const uint64_t da = umma_desc_k_sw128(a_addr);
-          const uint64_t db = umma_desc_k_sw128(b_addr);
+          const uint32_t b_addr = a_addr + kCgTapsPerStage * 128 * 128;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_f16(d_tmem, da + (ks * 32 >> 4), db + (ks * 32 >> 4), idesc, (kb | ks) != 0);
+          for (int kw = 0; kw < kCgTapsPerStage; ++kw) {
+            const uint64_t da = umma_desc_k_sw128(a_addr + kw * 128 * 128);
+            const uint64_t db = umma_desc_k_sw128(b_addr + kw * w_tile);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_f16(d_tmem, da + (ks * 32 >> 4), db + (ks * 32 >> 4), idesc, (kb | kw | ks) != 0);
+          }
           umma_commit(&empty[s]);
         }
         umma_commit(&tfull[ab]);
