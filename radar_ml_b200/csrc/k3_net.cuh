@@ -617,6 +617,8 @@ constexpr int kK5StageBytes = (kK5BlockM + kK5N) * kK5BlockK * 2;   // 24 576
 
 struct K5Params {
   int64_t B;
+  int kpg;                // 64-wide K blocks per ring stage (4, 2 or 1, dividing k_blocks): one barrier
+                          // round trip (~650 cycles, see k4_conv_igemm) then covers 4 x 4 UMMAs
   int k_blocks;           // K / 64
   int C;                  // classes
   int head;               // 0 softmax (dnn, sgan c_model), 1 Z/(Z+1) (sgan d_model)
@@ -687,20 +689,30 @@ k5_dense_stack(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // ring: n_st stages of kpg K blocks each (the same bytes in flight for every kpg)
+  const int kpg = p.kpg;
+  const int n_st = kK5Stages / kpg;
+  const int st_bytes = kpg * kK5StageBytes;
+  const int k_steps = p.k_blocks / kpg;
+  constexpr int kABytes = kK5BlockM * kK5BlockK * 2, kBBytes = kK5N * kK5BlockK * 2;
   if (warp == 0) {
     if (lane == 0) {
       const uint64_t pol_a = policy_evict_first();
       const uint64_t pol_b = policy_evict_last();
       uint32_t kit = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
-          const int s = kit % kK5Stages;
-          mbar_wait(&empty[s], ((kit / kK5Stages) & 1) ^ 1);
-          unsigned char* a_dst = smem + s * kK5StageBytes;
-          unsigned char* b_dst = a_dst + kK5BlockM * kK5BlockK * 2;
-          mbar_arrive_expect_tx(&full[s], kK5StageBytes);
-          tma_load_2d(a_dst, &map_act, kb * kK5BlockK, static_cast<int32_t>(tile * kK5BlockM), &full[s], pol_a);
-          tma_load_2d(b_dst, &map_w1, kb * kK5BlockK, 0, &full[s], pol_b);
+        for (int ks = 0; ks < k_steps; ++ks, ++kit) {
+          const int s = kit % n_st;
+          mbar_wait(&empty[s], ((kit / n_st) & 1) ^ 1);
+          unsigned char* a_dst = smem + s * st_bytes;
+          unsigned char* b_dst = a_dst + kpg * kABytes;
+          mbar_arrive_expect_tx(&full[s], st_bytes);
+          for (int g = 0; g < kpg; ++g) {
+            const int kb = ks * kpg + g;
+            tma_load_2d(a_dst + g * kABytes, &map_act, kb * kK5BlockK, static_cast<int32_t>(tile * kK5BlockM),
+                        &full[s], pol_a);
+            tma_load_2d(b_dst + g * kBBytes, &map_w1, kb * kK5BlockK, 0, &full[s], pol_b);
+          }
         }
       }
     }
@@ -713,17 +725,19 @@ k5_dense_stack(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         mbar_wait(&tempty[ab], ((ait >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * kK5N;
-        for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
-          const int s = kit % kK5Stages;
-          mbar_wait(&full[s], (kit / kK5Stages) & 1);
+        for (int ks = 0; ks < k_steps; ++ks, ++kit) {
+          const int s = kit % n_st;
+          mbar_wait(&full[s], (kit / n_st) & 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * kK5StageBytes);
-          const uint32_t b_addr = a_addr + kK5BlockM * kK5BlockK * 2;
-          const uint64_t da = umma_desc_k_sw128(a_addr);
-          const uint64_t db = umma_desc_k_sw128(b_addr);
+          const uint32_t a_addr = smem_u32(smem + s * st_bytes);
+          const uint32_t b_addr = a_addr + kpg * kABytes;
+          for (int g = 0; g < kpg; ++g) {
+            const uint64_t da = umma_desc_k_sw128(a_addr + g * kABytes);
+            const uint64_t db = umma_desc_k_sw128(b_addr + g * kBBytes);
 #pragma unroll
-          for (int ks = 0; ks < kK5BlockK / 16; ++ks)   // UMMA_K = 16 bf16 = 32 bytes
-            umma_f16(d_tmem, da + (ks * 32 >> 4), db + (ks * 32 >> 4), idesc, (kb | ks) != 0);
+            for (int k16 = 0; k16 < kK5BlockK / 16; ++k16)   // UMMA_K = 16 bf16 = 32 bytes
+              umma_f16(d_tmem, da + (k16 * 32 >> 4), db + (k16 * 32 >> 4), idesc, (ks | g | k16) != 0);
+          }
           umma_commit(&empty[s]);
         }
         umma_commit(&tfull[ab]);

@@ -1463,6 +1463,8 @@ static int net_dense(rml_ctx* c, const uint16_t* flat, int64_t n_scans, float* p
   if (rc) return rc;
   K5Params kp;
   kp.B = n_scans; kp.k_blocks = n.K / kK5BlockK; kp.C = n.C; kp.head = n.head;
+  kp.kpg = (kp.k_blocks % 4 == 0) ? 4 : (kp.k_blocks % 2 == 0) ? 2 : 1;
+  if (const char* e = getenv("RML_K5_KPG")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && kp.k_blocks % v == 0) kp.kpg = v; }
   kp.act1 = n.act1; kp.act2 = n.act2; kp.alpha = n.alpha;
   kp.b1 = n.b1; kp.w2 = n.w2; kp.b2 = n.b2; kp.w3 = n.w3; kp.b3 = n.b3;
   kp.proba = proba; kp.logits = logits; kp.label = label;
