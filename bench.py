@@ -40,6 +40,27 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE line, the JSON result.  Native libraries write to file descriptor 1
+# behind Python's back (NCCL prints "NCCL version ..." there even with NCCL_DEBUG_FILE set), so fd 1
+# is pointed at stderr for the whole run and the result goes out through a private copy of the
+# original stdout.
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -183,7 +204,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -291,9 +312,9 @@ def run_ours(args):
 
     if args.skip_extras:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world,
-                              "ms_per_step": ms / args.steps, "k1_ms": k1_ms, "k2_exposed_ms": k2_ms, "fused": bool(fused),
-                              "note": "--skip-extras profiling run, not a bench line"}), flush=True)
+            emit({"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world,
+                  "ms_per_step": ms / args.steps, "k1_ms": k1_ms, "k2_exposed_ms": k2_ms, "fused": bool(fused),
+                  "note": "--skip-extras profiling run, not a bench line"})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -459,7 +480,7 @@ def run_ours(args):
             line["general_precision"] = general
         if u8leg:
             line["u8_cubes"] = u8leg
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -475,6 +496,7 @@ def main():
     ap.add_argument("--skip-extras", action="store_true",
                     help="profiling aid: skip the e2e, parity and cpu_baseline legs")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
