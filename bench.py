@@ -361,6 +361,24 @@ def run_ours(args):
             cpu = {"value": v, "unit": "scans/s", "cores": used, "kind": "port",
                    "sample": "%d of the GPU-scored scans, per-scan predict.py loop, one process per "
                              "core, sklearn libsvm (%.1f s)" % (sample, dt)}
+            # second, independent checker: the plain-C oracle (OpenMP over scans) on the same sample —
+            # a wider parity check than the 192 numpy-oracle scans, and a best-effort all-cores CPU time
+            try:
+                from oracle import c_oracle
+                cm = c_oracle.CModel(p)
+                c_oracle.scan_path(host_np[:64], cm)
+                t0 = time.perf_counter()
+                _, lab_c, _, known_c, P_c = c_oracle.scan_path(host_np[:sample], cm, mode="max")
+                dtc = time.perf_counter() - t0
+                parity["c_oracle"] = {
+                    "scans": sample,
+                    "labels_equal": bool(np.array_equal(label[:sample].cpu().numpy(), lab_c)),
+                    "known_equal": bool(np.array_equal(known[:sample].cpu().numpy().astype(bool), known_c)),
+                    "max_abs_dproba": float(np.abs(proba[:sample].cpu().numpy().astype(np.float64) - P_c).max())}
+                cpu["c_port"] = {"value": sample / dtc, "unit": "scans/s", "cores": cores,
+                                 "sample": "%d scans, oracle/c/radar_oracle.c, OpenMP over scans (%.1f s)" % (sample, dtc)}
+            except Exception as e:      # the checker's checker must never take the bench line down
+                parity["c_oracle"] = {"error": repr(e)}
 
     # ---- general-precision case: real-valued cubes + non-integral support vectors
     general = None
