@@ -897,9 +897,12 @@ int predict_host_impl(rml_ctx* c, const void* cubes_host, int cube_u8, int64_t B
   const int64_t chunk = cube_u8 ? 1024 : 512;
   const size_t cube_bytes = static_cast<size_t>(c->sx) * c->sy * c->sz * (cube_u8 ? 1 : 4);
   const int C = c->model.C;
-  if (hp.chunk != chunk || hp.cube_bytes != cube_bytes) {
+  // the feature staging depends on the loaded model (u8 rows vs float32 rows): a model change
+  // after the first call must not leave a workspace that is too small
+  const size_t work_need = rml_predict_workspace_bytes(c, chunk);
+  if (hp.chunk != chunk || hp.cube_bytes != cube_bytes || hp.work_bytes < work_need) {
     free_pipe(hp);
-    hp.work_bytes = rml_predict_workspace_bytes(c, chunk);
+    hp.work_bytes = work_need;
     for (int i = 0; i < kHostBufs; ++i) {
       RML_CUDA(c, cudaMalloc(&hp.cubes[i], chunk * cube_bytes));
       RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.ijk[i]), chunk * 3 * 4));
@@ -912,6 +915,9 @@ int predict_host_impl(rml_ctx* c, const void* cubes_host, int cube_u8, int64_t B
     hp.chunk = chunk;
     hp.cube_bytes = cube_bytes;
   }
+  // the general-precision scorer keeps one grow-only scratch per context (dg_planes): chunks of
+  // such a model must not overlap on different streams, so they all take slot 0
+  const int n_slots = use_u8_path(c) ? kHostBufs : 1;
   const char* src = static_cast<const char*>(cubes_host);
   int64_t done = 0;
   int slot = 0;
@@ -930,7 +936,7 @@ int predict_host_impl(rml_ctx* c, const void* cubes_host, int cube_u8, int64_t B
     if (known_host)
       RML_CUDA(c, cudaMemcpyAsync(known_host + done, hp.known[slot], n, cudaMemcpyDeviceToHost, st));
     done += n;
-    slot = (slot + 1) % kHostBufs;
+    slot = (slot + 1) % n_slots;
   }
   for (int i = 0; i < kHostBufs; ++i) RML_CUDA(c, cudaStreamSynchronize(hp.stream[i]));
   return RML_OK;
