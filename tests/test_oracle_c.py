@@ -104,3 +104,35 @@ def test_c_oracle_linear_masks_and_index_errors():
         c_oracle.project(cubes[0], "slice", (0, 0, -177))
     with pytest.raises(IndexError):
         cubes[0][:, :, -177]            # what numpy (the reference) does with the same index
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_c_oracle_random_arenas_models_and_values(seed):
+    """Seeded random arenas (odd sizes), real-valued / negative voxels, random calibrated models with
+    2..6 classes: the two restatements must agree everywhere the reference's arithmetic is defined."""
+    rng = np.random.default_rng(100 + seed)
+    sx, sy, sz = (int(v) for v in rng.integers(2, 13, size=3))
+    n = 17
+    cubes = rng.normal(40.0, 70.0, size=(n, sx, sy, sz)).astype(np.float32)
+    if seed % 2:
+        cubes = np.rint(np.clip(cubes, 0, 255)).astype(np.float32)
+    ijk = np.stack([rng.integers(-d, d, size=n) for d in (sx, sy, sz)], axis=1).astype(np.int32)
+    mask = [(True, True, True), (True, False, True), (False, True, False), (False, False, True),
+            (True, True, False), (False, True, True)][seed]
+    F = (sx * sz if mask[0] else 0) + (sy * sz if mask[1] else 0) + (sx * sy if mask[2] else 0)
+    C = 2 + seed % 5
+    n_support = rng.integers(1, 5, size=C).astype(np.int32)
+    n_sv = int(n_support.sum())
+    p = restate.SvcParams(
+        n_classes=C, gamma=float(rng.uniform(1e-4, 5e-2)),
+        sv=rng.uniform(0, 1, size=(n_sv, F)), dual_coef=rng.normal(0, 2, size=(C - 1, n_sv)),
+        rho=rng.normal(0, 1, size=C * (C - 1) // 2), n_support=n_support,
+        platt_a=rng.normal(-1.5, 0.5, size=(1 if C == 2 else C)),
+        platt_b=rng.normal(0, 0.5, size=(1 if C == 2 else C)), classes=np.arange(C))
+    for mode, ij in (("max", None), ("slice", ijk)):
+        Xn, labn, prn, knownn, Pn = restate.scan_path(cubes, p, mode=mode, ijk=ij, mask=restate.ProjMask(*mask))
+        Xc, labc, prc, knownc, Pc = c_oracle.scan_path(cubes, p, mode=mode, ijk=ij, mask=mask)
+        assert Xn.dtype == Xc.dtype == np.float32 and np.array_equal(Xn, Xc)
+        assert np.abs(Pn - Pc).max() < 1e-12
+        assert np.array_equal(labn, labc) and np.array_equal(knownn, knownc)
+        assert np.abs(Pc.sum(axis=1) - 1.0).max() < 1e-12
