@@ -69,9 +69,22 @@ int rml_set_arena_bounds(rml_ctx* ctx, double r_min, double r_max, double theta_
 int rml_feature_len(const rml_ctx* ctx, uint32_t mask);    /* F for a mask (10010 for all)   */
 int rml_feature_stride(const rml_ctx* ctx, uint32_t mask, int dtype); /* elements per row    */
 
-/* Per-feature affine (x - offset) / scale applied by rml_project for RML_F32 output.
- * scalar form covers common.py:148 (/255., offset 0) and dnn.py:202-205 ((p-127.5)/127.5). */
+/* Affine (x - offset) / scale applied by rml_project for RML_F32 output, as an IEEE float32 true
+ * division.  The scalar form covers common.py:148 (/255., offset 0) and dnn.py:202-205
+ * ((p-127.5)/127.5). */
 int rml_set_affine(rml_ctx* ctx, float offset, float scale, int enabled);
+/* Per-feature form, SURVEY.md §8b: offset_host[F], scale_host[F] (a fitted StandardScaler's mean_
+ * and scale_ — what BASELINE.json north_star calls "StandardScaler-normalised"; the reference
+ * itself only divides by RADAR_MAX, common.py:148, which stays the default).  NULL, NULL restores
+ * that default.  With tables loaded every float32 feature producer (rml_project, rml_predict*,
+ * rml_process_samples*) emits (x - offset[f]) / scale[f]; the integer u8 operand rows cannot
+ * carry a per-feature scale, so rml_predict* switch to float32 features and the exact
+ * multi-digit tensor-core scorer (or the float64 scorer) — load the affine BEFORE the model. */
+int rml_load_affine(rml_ctx* ctx, const float* offset_host, const float* scale_host, int F);
+/* force_f32 = 1: rml_predict* emit float32 features and score them with the multi-digit /
+ * float64 scorer even when the model qualifies for the u8 path — the path real-valued cubes
+ * need (the u8 path reports them with RML_E_NONINTEGRAL instead of scoring them). 0 = automatic. */
+int rml_set_precision(rml_ctx* ctx, int force_f32);
 
 /* ---- model load: what predict.py:224-225 unpickles ------------------------------------ */
 /* CalibratedClassifierCV(prefit SVC rbf) built at train.py:478-479, 723-724.
@@ -147,7 +160,10 @@ int rml_quantize_features(rml_ctx* ctx, const float* feats_dev, int64_t B, int F
                           uint8_t* feats_u8_dev, int32_t* norms_dev, rml_stream stream);
 
 /* ---- K1 -> K2 fused pipeline: one predict.py:93-119 iteration for B scans -------------- */
-/* workspace: rml_predict_workspace_bytes(ctx, B) bytes of device memory (feature staging). */
+/* workspace: rml_predict_workspace_bytes(ctx, B) bytes of 256-byte aligned device memory for the
+ * loaded model (feature staging, norms, digit planes of the float32 path, tile counters of the
+ * co-resident pipeline): rml_predict* allocate nothing.  label_dev may point into a larger
+ * gather buffer (see rml_allgather_labels). */
 size_t rml_predict_workspace_bytes(const rml_ctx* ctx, int64_t B);
 int rml_predict(rml_ctx* ctx, const float* cubes_dev, int64_t B, int mode, const int32_t* ijk_dev,
                 uint32_t mask, double min_proba, void* workspace_dev, float* proba_dev,
@@ -158,6 +174,42 @@ int rml_predict(rml_ctx* ctx, const float* cubes_dev, int64_t B, int mode, const
 int rml_predict_host(rml_ctx* ctx, const float* cubes_host, int64_t B, int mode,
                      const int32_t* ijk_host, uint32_t mask, double min_proba, float* proba_host,
                      int32_t* label_host, uint8_t* known_host);
+
+/* Buffers the library owns are created here, never inside a hot entry point (SURVEY.md §8b
+ * ownership row): call after the model is loaded, again after loading another model.
+ *   RML_RESERVE_SCORE    digit-plane scratch so rml_score accepts float32 rows of up to max_batch
+ *   RML_RESERVE_HOST     chunked staging of rml_predict_host (float32 cubes)
+ *   RML_RESERVE_HOST_U8  the same for rml_predict_host_u8
+ *   RML_RESERVE_SMALL    staging of rml_score_host / rml_predict_targets_host for max_batch rows */
+enum { RML_RESERVE_SCORE = 1, RML_RESERVE_HOST = 2, RML_RESERVE_HOST_U8 = 4, RML_RESERVE_SMALL = 8 };
+int rml_reserve(rml_ctx* ctx, int64_t max_batch, int flags);
+
+/* predict.py:56-70 classifier() for HOST features: feats_host float32 [B][F] as
+ * common.process_samples(scale=True) returns them -> predict_proba, argmax, >= min_proba.  The
+ * scorer is chosen on the device: u8 tensor-core scorer for integral rows of an integral model,
+ * else the multi-digit tensor-core scorer, else float64; one synchronisation in the common case. */
+int rml_score_host(rml_ctx* ctx, const float* feats_host, int64_t B, double min_proba,
+                   float* proba_host, int32_t* label_host, uint8_t* known_host);
+/* One predict.py:93-119 iteration — the reference's live loop body: ONE raw cube (predict.py:90-91,
+ * float32 [size_x][size_y][size_z], host) and the T targets GetSensorTargets reported for it
+ * (ijk_host int32 [T][3], common.py:106-121).  The cube is uploaded once. */
+int rml_predict_targets_host(rml_ctx* ctx, const float* cube_host, int T, const int32_t* ijk_host,
+                             uint32_t mask, double min_proba, float* proba_host,
+                             int32_t* label_host, uint8_t* known_host);
+
+/* ---- multi-GPU: the one exchange of the path ----------------------------- */
+/* One context per GPU/process.  rank 0 calls rml_comm_unique_id (128 bytes), hands the id to the
+ * other ranks by any host channel, every rank calls rml_comm_init.  NCCL is dlopen'ed
+ * (libnccl.so.2 — the copy already in the process if there is one, e.g. torch's; env
+ * RML_NCCL_LIB overrides); a single-GPU process never needs it. */
+int rml_comm_unique_id(rml_ctx* ctx, void* id128_host);
+int rml_comm_init(rml_ctx* ctx, int rank, int world, const void* id128_host);
+int rml_comm_destroy(rml_ctx* ctx);
+/* ncclAllGather of int32 labels on `stream`: recv_dev [world][count].  send_dev may be
+ * recv_dev + rank*count (in place): pass that slice as rml_predict's label_dev and the scorer
+ * writes straight into the gather buffer.  world == 1 without a communicator degenerates to a copy. */
+int rml_allgather_labels(rml_ctx* ctx, const int32_t* send_dev, int32_t* recv_dev, int64_t count,
+                         rml_stream stream);
 
 /* ---- uint8 cubes: the sensor's integers kept as bytes ----------------------------------- */
 /* predict.py:90-91 widens the Walabot's integer voxels (0..255, ground_truth_samples.py:352)

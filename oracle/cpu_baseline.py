@@ -28,7 +28,7 @@ def scan_loop(cubes, cal, classes, mode="max", ijk=None, min_proba=0.7):
     zoom = restate.calc_proj_zoom(22, 31, 176, 22, 31, 176)
     for s in range(cubes.shape[0]):
         t = restate.project(cubes[s], mode, None if ijk is None else tuple(int(v) for v in ijk[s]))
-        obs = restate.process_samples([t], proj_mask=mask, proj_zoom=zoom, scale=True)
+        obs = restate.process_samples([t], proj_mask=mask, proj_zoom=zoom, scale=True, always_zoom=True)
         preds = cal.predict_proba(obs.reshape(1, -1))[0]     # predict.py:60
         j = int(np.argmax(preds))
         names.append(classes[j] if preds[j] >= min_proba else "Unknown")
@@ -80,11 +80,30 @@ def run_all_cores(cubes, cal, classes, mode="max", cores=None, repeats=1):
     return n / best, best, len(chunks)
 
 
-def run_one_core(cubes, cal, classes, mode="max"):
+def run_one_core(cubes, cal, classes, mode="max", repeats=3):
+    """The reference-exact loop on ONE core (what predict.py does); best of ``repeats`` passes.
+    Returns (scans/s, seconds of the best pass, median per-scan latency in ms)."""
+    best, lat = None, []
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         scan_loop(cubes[:1], cal, classes, mode)
-        t0 = time.perf_counter()
-        scan_loop(cubes, cal, classes, mode)
-        dt = time.perf_counter() - t0
-    return cubes.shape[0] / dt, dt
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            for s in range(cubes.shape[0]):
+                t1 = time.perf_counter()
+                scan_loop(cubes[s:s + 1], cal, classes, mode)
+                lat.append(time.perf_counter() - t1)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return cubes.shape[0] / best, best, 1e3 * float(np.median(lat))
+
+
+def cpu_model_string():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:  # pragma: no cover
+        pass
+    return "unknown"

@@ -72,17 +72,20 @@ def project(cube: np.ndarray, mode: str, ijk=None):
 
 
 def process_samples(samples, proj_mask=ProjMask(True, True, True),
-                    proj_zoom=ProjZoom([1.0, 1.0], [1.0, 1.0], [1.0, 1.0]), scale=False):
+                    proj_zoom=ProjZoom([1.0, 1.0], [1.0, 1.0], [1.0, 1.0]), scale=False,
+                    always_zoom=False):
     """common.py:123-149.  ndimage.zoom(order=3) is an exact identity at zoom 1.0
-    (checked against the reference in tests/test_oracle.py); other factors go through scipy,
-    exactly like the reference."""
+    (checked against the reference in tests/test_oracle.py), so the parity oracle skips it there;
+    other factors go through scipy, exactly like the reference.  ``always_zoom=True`` calls
+    ndimage.zoom unconditionally like common.py:143 does (the spline prefilter runs even at
+    1.0): the CPU TIMING arm uses it so that the reference's cost is not understated."""
     def make(t):
         wanted = []
         for idx, p in enumerate(t):
             if not proj_mask[idx]:
                 continue
             z = proj_zoom[idx]
-            if float(z[0]) == 1.0 and float(z[1]) == 1.0:
+            if not always_zoom and float(z[0]) == 1.0 and float(z[1]) == 1.0:
                 wanted.append(np.asarray(p))
             else:
                 from scipy import ndimage

@@ -20,6 +20,7 @@ OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMODEL, E_NONINTEGRAL, E_RANGE = 0, -1,
 MODE_MAX, MODE_SLICE = 0, 1
 MASK_XZ, MASK_YZ, MASK_XY, MASK_ALL = 1, 2, 4, 7
 F32, U8, F32_EXACT = 0, 1, 2
+RESERVE_SCORE, RESERVE_HOST, RESERVE_HOST_U8, RESERVE_SMALL = 1, 2, 4, 8
 
 
 class RadarMLError(RuntimeError):
@@ -39,7 +40,7 @@ class OutOfRangeInput(RadarMLError):
 def nvcc_command(out=LIB_PATH):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     return [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-            "-Xcompiler", "-fPIC", "-shared", "-o", out, SRC]
+            "-Xcompiler", "-fPIC", "-shared", "-o", out, SRC, "-ldl"]
 
 
 def build(force=False, verbose=False):
@@ -71,6 +72,15 @@ SIGNATURES = {
     "rml_feature_len": (C.c_int, [_vp, _u32]),
     "rml_feature_stride": (C.c_int, [_vp, _u32, C.c_int]),
     "rml_set_affine": (C.c_int, [_vp, _f32, _f32, C.c_int]),
+    "rml_load_affine": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "rml_set_precision": (C.c_int, [_vp, C.c_int]),
+    "rml_reserve": (C.c_int, [_vp, _i64, C.c_int]),
+    "rml_score_host": (C.c_int, [_vp, _vp, _i64, _f64, _vp, _vp, _vp]),
+    "rml_predict_targets_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _u32, _f64, _vp, _vp, _vp]),
+    "rml_comm_unique_id": (C.c_int, [_vp, _vp]),
+    "rml_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "rml_comm_destroy": (C.c_int, [_vp]),
+    "rml_allgather_labels": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "rml_load_svc_rbf": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _f64, _vp,
                                    _vp, _f64]),
     "rml_load_linear": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _f64]),

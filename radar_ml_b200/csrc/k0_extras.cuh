@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "k1_project.cuh"
 #include "ptx.cuh"
 
 namespace rml {
@@ -21,6 +22,7 @@ struct DeriveParams {
   const float* cubes;
   int32_t* ijk;       // [B][T][3], ascending by axis sum like np.argsort (last = strongest)
   float* sums;        // nullable: [B][sx+sy+sz] axis sums (theta | phi | r)
+  unsigned int* status;  // [3] += scans whose axis sums had no finite maximum
   int64_t B;
   int sx, sy, sz, T;
 };
@@ -120,6 +122,13 @@ __global__ void __launch_bounds__(256) k0_derive_targets(const DeriveParams p) {
           if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
         if (lane == 0) {
+          if (bi >= n) {
+            // no candidate compared greater than -FLT_MAX (NaN or -inf sums): take the lowest
+            // unused index instead of the sentinel and report it (status[3] -> RML_E_INVALID)
+            bi = 0;
+            while (bi < n - 1 && S[bi] == -FLT_MAX) ++bi;
+            if (p.status) atomicAdd(p.status + 3, 1u);
+          }
           // rank t from the top goes to slot T-1-t (ascending order of the reference)
           p.ijk[(b * p.T + (p.T - 1 - t)) * 3 + warp] = bi;
           S[bi] = -FLT_MAX;
@@ -144,6 +153,8 @@ struct ZoomParams {
   int F;
   int scale;
   float offset, scale_value;
+  const float* aff_off;   // nullable per-feature tables (indexed by output feature)
+  const float* aff_scl;
 };
 
 // grid (scans, 3); smem: P [ih][iw] f32 | T [ih][ow] f64
@@ -173,7 +184,7 @@ __global__ void __launch_bounds__(256) k0_zoom_concat(const ZoomParams p) {
       double s = 0.0;
       for (int r = 0; r < ih; ++r) s = fma(ar[orow * ih + r], T[r * ow + oc], s);
       const float v = static_cast<float>(s);                 // ndimage.zoom returns the input dtype
-      out[e] = p.scale ? __fdiv_rn(v - p.offset, p.scale_value) : v;
+      out[e] = p.scale ? affine_apply(v, p.offset, p.scale_value, p.aff_off, p.aff_scl, p.off[q] + e) : v;
     }
     __syncthreads();
   }

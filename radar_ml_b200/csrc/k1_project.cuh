@@ -47,10 +47,30 @@ struct K1Params {
   uint32_t mask;
   float offset, scale;  // f32 output: (v - offset) / scale when affine != 0
   int affine;
+  const float* aff_off;  // nullable: per-feature offset[F] / scale[F] tables (rml_load_affine, a fitted
+  const float* aff_scl;  // StandardScaler's mean_ / scale_); they replace the scalar pair
   int split;                // bulk copies per slab (1; 2 / 4 are tuning experiments)
   unsigned int* tile_done;  // nullable: [ceil(B/128)] += 1 per finished scan (u8 path) so a
                             // co-resident scorer can start on a 128-scan tile as soon as it is whole
 };
+
+// np.max propagates NaN; fmaxf drops it.  max.NaN.f32 (FMNMX.NAN) costs the same instruction.
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float warp_max_nan_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.NaN.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+// (v - offset) / scale as an IEEE float32 true division (common.py:148: x/255f != x*(1/255f) for
+// 126 of the 256 integers); per-feature tables when loaded
+__device__ __forceinline__ float affine_apply(float v, float offset, float scale, const float* off,
+                                              const float* scl, int idx) {
+  return off ? __fdiv_rn(v - __ldg(off + idx), __ldg(scl + idx)) : __fdiv_rn(v - offset, scale);
+}
 
 template <typename OutT>
 struct Emit;
@@ -79,17 +99,16 @@ struct Emit<uint8_t> {
 
 template <>
 struct Emit<float> {
-  static __device__ __forceinline__ float cvt(float v, const K1Params& p) {
-    // common.py:148 is an IEEE float32 true division (x/255f != x*(1/255f) for 126 of 256 ints)
-    return p.affine ? __fdiv_rn(v - p.offset, p.scale) : v;
+  static __device__ __forceinline__ float cvt(float v, const K1Params& p, int idx) {
+    return p.affine ? affine_apply(v, p.offset, p.scale, p.aff_off, p.aff_scl, idx) : v;
   }
   static __device__ __forceinline__ void put2(float* stg, int idx, float a, float b,
                                               const K1Params& p, uint32_t&, uint32_t&) {
-    *reinterpret_cast<float2*>(stg + idx) = make_float2(cvt(a, p), cvt(b, p));
+    *reinterpret_cast<float2*>(stg + idx) = make_float2(cvt(a, p, idx), cvt(b, p, idx + 1));
   }
   static __device__ __forceinline__ void put1(float* stg, int idx, float a, const K1Params& p,
                                               uint32_t&, uint32_t&) {
-    stg[idx] = cvt(a, p);
+    stg[idx] = cvt(a, p, idx);
   }
 };
 
@@ -141,16 +160,16 @@ __device__ __forceinline__ void k1_row_warp(const K1Params& p, const float* slab
       float m[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
-        yz[r][0] = fmaxf(yz[r][0], a[r].x);
-        yz[r][1] = fmaxf(yz[r][1], a[r].y);
-        yz[r][2] = fmaxf(yz[r][2], c[r].x);
-        yz[r][3] = fmaxf(yz[r][3], c[r].y);
-        yz[r][4] = fmaxf(yz[r][4], e[r].x);
-        yz[r][5] = fmaxf(yz[r][5], e[r].y);
-        m[r] = fmaxf(fmaxf(fmaxf(a[r].x, a[r].y), fmaxf(c[r].x, c[r].y)), fmaxf(e[r].x, e[r].y));
+        yz[r][0] = max_nan(yz[r][0], a[r].x);
+        yz[r][1] = max_nan(yz[r][1], a[r].y);
+        yz[r][2] = max_nan(yz[r][2], c[r].x);
+        yz[r][3] = max_nan(yz[r][3], c[r].y);
+        yz[r][4] = max_nan(yz[r][4], e[r].x);
+        yz[r][5] = max_nan(yz[r][5], e[r].y);
+        m[r] = max_nan(max_nan(max_nan(a[r].x, a[r].y), max_nan(c[r].x, c[r].y)), max_nan(e[r].x, e[r].y));
       }
 #pragma unroll
-      for (int r = 0; r < NR; ++r) m[r] = warp_max_f32(m[r]);
+      for (int r = 0; r < NR; ++r) m[r] = warp_max_nan_f32(m[r]);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);    // the slab has been consumed
       // lane r stores the xy value of row r: one conversion per slab instead of NR
@@ -252,12 +271,12 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
             const float2 cc = row[32 + lane];
             float2 e = make_float2(NEG, NEG);
             if (lane < 24) e = row[64 + lane];
-            m0 = fmaxf(m0, a.x);
-            m1 = fmaxf(m1, a.y);
-            m2 = fmaxf(m2, cc.x);
-            m3 = fmaxf(m3, cc.y);
-            m4 = fmaxf(m4, e.x);
-            m5 = fmaxf(m5, e.y);
+            m0 = max_nan(m0, a.x);
+            m1 = max_nan(m1, a.y);
+            m2 = max_nan(m2, cc.x);
+            m3 = max_nan(m3, cc.y);
+            m4 = max_nan(m4, e.x);
+            m5 = max_nan(m5, e.y);
           }
           const int base = off_xz + i * kSZ + 2 * lane;
           Emit<OutT>::put2(stg, base, m0, m1, p, sumsq, bad);
@@ -343,7 +362,11 @@ struct K1GenParams {
   uint32_t mask;
   float offset, scale;
   int affine;
+  const float* aff_off;   // nullable per-feature tables, see K1Params
+  const float* aff_scl;
   int mode;
+  int64_t cube_stride;    // elements between consecutive scans' cubes; 0 = every row reads cube 0
+                          // (one scan, T targets: predict.py:93-119)
 };
 
 template <typename OutT>
@@ -360,7 +383,7 @@ __device__ __forceinline__ void gen_put<uint8_t>(uint8_t* out, int idx, float v,
 template <>
 __device__ __forceinline__ void gen_put<float>(float* out, int idx, float v, const K1GenParams& p,
                                                uint32_t&, uint32_t&) {
-  out[idx] = p.affine ? __fdiv_rn(v - p.offset, p.scale) : v;
+  out[idx] = p.affine ? affine_apply(v, p.offset, p.scale, p.aff_off, p.aff_scl, idx) : v;
 }
 
 template <typename OutT, typename InT = float>
@@ -373,7 +396,7 @@ __global__ void __launch_bounds__(256) k1_project_generic(const K1GenParams p) {
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     if (threadIdx.x == 0) s_sum = 0;
     __syncthreads();
-    const InT* cube = static_cast<const InT*>(p.cubes) + b * static_cast<int64_t>(sx) * sy * sz;
+    const InT* cube = static_cast<const InT*>(p.cubes) + b * p.cube_stride;
     OutT* out = reinterpret_cast<OutT*>(p.feats) + b * static_cast<int64_t>(p.stride);
     uint32_t sumsq = 0, bad = 0;
     int ti = 0, tj = 0, tk = 0;
@@ -400,7 +423,7 @@ __global__ void __launch_bounds__(256) k1_project_generic(const K1GenParams p) {
           v = static_cast<float>(cube[(static_cast<int64_t>(i) * sy + tj) * sz + k]);
         } else {
           v = -FLT_MAX;
-          for (int j = 0; j < sy; ++j) v = fmaxf(v, static_cast<float>(cube[(static_cast<int64_t>(i) * sy + j) * sz + k]));
+          for (int j = 0; j < sy; ++j) v = max_nan(v, static_cast<float>(cube[(static_cast<int64_t>(i) * sy + j) * sz + k]));
         }
         gen_put<OutT>(out, e, ok ? v : 0.f, p, sumsq, bad);
       }
@@ -413,7 +436,7 @@ __global__ void __launch_bounds__(256) k1_project_generic(const K1GenParams p) {
           v = static_cast<float>(cube[(static_cast<int64_t>(ti) * sy + j) * sz + k]);
         } else {
           v = -FLT_MAX;
-          for (int i = 0; i < sx; ++i) v = fmaxf(v, static_cast<float>(cube[(static_cast<int64_t>(i) * sy + j) * sz + k]));
+          for (int i = 0; i < sx; ++i) v = max_nan(v, static_cast<float>(cube[(static_cast<int64_t>(i) * sy + j) * sz + k]));
         }
         gen_put<OutT>(out, off_yz + e, ok ? v : 0.f, p, sumsq, bad);
       }
@@ -430,8 +453,8 @@ __global__ void __launch_bounds__(256) k1_project_generic(const K1GenParams p) {
         for (int e = warp; e < fxy; e += nw) {
           const InT* row = cube + static_cast<int64_t>(e) * sz;
           float v = -FLT_MAX;
-          for (int k = lane; k < sz; k += 32) v = fmaxf(v, static_cast<float>(row[k]));
-          v = warp_max_f32(v);
+          for (int k = lane; k < sz; k += 32) v = max_nan(v, static_cast<float>(row[k]));
+          v = warp_max_nan_f32(v);
           if (lane == 0) gen_put<OutT>(out, off_xy + e, v, p, sumsq, bad);
         }
       }
@@ -467,8 +490,10 @@ template <>
 __device__ __forceinline__ void slice_put4<float>(float* out, int idx, float4 v, const K1GenParams& p,
                                                   uint32_t&, uint32_t&) {
   if (p.affine) {
-    v.x = __fdiv_rn(v.x - p.offset, p.scale); v.y = __fdiv_rn(v.y - p.offset, p.scale);
-    v.z = __fdiv_rn(v.z - p.offset, p.scale); v.w = __fdiv_rn(v.w - p.offset, p.scale);
+    v.x = affine_apply(v.x, p.offset, p.scale, p.aff_off, p.aff_scl, idx);
+    v.y = affine_apply(v.y, p.offset, p.scale, p.aff_off, p.aff_scl, idx + 1);
+    v.z = affine_apply(v.z, p.offset, p.scale, p.aff_off, p.aff_scl, idx + 2);
+    v.w = affine_apply(v.w, p.offset, p.scale, p.aff_off, p.aff_scl, idx + 3);
   }
   out[idx] = v.x; out[idx + 1] = v.y; out[idx + 2] = v.z; out[idx + 3] = v.w;   // rows are 8-B aligned only
 }
@@ -500,7 +525,7 @@ __global__ void __launch_bounds__(256) k1_project_slice(const K1GenParams p) {
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     if (threadIdx.x == 0) s_sum = 0;
     __syncthreads();
-    const InT* cube = static_cast<const InT*>(p.cubes) + b * static_cast<int64_t>(sx) * sy * sz;
+    const InT* cube = static_cast<const InT*>(p.cubes) + b * p.cube_stride;
     OutT* out = reinterpret_cast<OutT*>(p.feats) + b * static_cast<int64_t>(p.stride);
     int ti = p.ijk[b * 3 + 0], tj = p.ijk[b * 3 + 1], tk = p.ijk[b * 3 + 2];
     if (ti < 0) ti += sx;                       // numpy: negative indices wrap once
@@ -553,6 +578,8 @@ struct PsParams {
   int F;
   int scale;
   float offset, scale_value;   // (v - offset) / scale_value when scale != 0
+  const float* aff_off;        // nullable per-feature tables, see K1Params
+  const float* aff_scl;
 };
 __global__ void __launch_bounds__(256) k1_process_samples(const PsParams p) {
   const int64_t total = p.B * static_cast<int64_t>(p.F);
@@ -565,7 +592,7 @@ __global__ void __launch_bounds__(256) k1_process_samples(const PsParams p) {
     for (int q = 0; q < 3; ++q)
       if (p.proj[q] && f >= p.off[q] && f < p.off[q] + p.len[q])
         v = p.proj[q][b * p.len[q] + (f - p.off[q])];
-    p.feats[e] = p.scale ? __fdiv_rn(v - p.offset, p.scale_value) : v;
+    p.feats[e] = p.scale ? affine_apply(v, p.offset, p.scale_value, p.aff_off, p.aff_scl, f) : v;
   }
 }
 

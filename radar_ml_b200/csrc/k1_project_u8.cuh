@@ -35,6 +35,8 @@ struct K1U8Params {
   uint32_t mask;
   float offset, scale;    // f32 output: (v - offset) / scale when affine != 0
   int affine;
+  const float* aff_off;   // nullable per-feature tables, see K1Params
+  const float* aff_scl;
   unsigned int* tile_done;  // nullable, see K1Params
 };
 
@@ -58,22 +60,22 @@ struct EmitB<uint8_t> {
 
 template <>
 struct EmitB<float> {
-  static __device__ __forceinline__ float cvt(uint32_t b, const K1U8Params& p) {
+  static __device__ __forceinline__ float cvt(uint32_t b, const K1U8Params& p, int idx) {
     const float v = static_cast<float>(b);
-    return p.affine ? __fdiv_rn(v - p.offset, p.scale) : v;
+    return p.affine ? affine_apply(v, p.offset, p.scale, p.aff_off, p.aff_scl, idx) : v;
   }
-  static __device__ __forceinline__ float4 cvt4(uint32_t w, const K1U8Params& p) {
-    return make_float4(cvt(w & 255u, p), cvt((w >> 8) & 255u, p), cvt((w >> 16) & 255u, p),
-                       cvt(w >> 24, p));
+  static __device__ __forceinline__ float4 cvt4(uint32_t w, const K1U8Params& p, int idx) {
+    return make_float4(cvt(w & 255u, p, idx), cvt((w >> 8) & 255u, p, idx + 1), cvt((w >> 16) & 255u, p, idx + 2),
+                       cvt(w >> 24, p, idx + 3));
   }
   static __device__ __forceinline__ void put8(float* stg, int idx, uint2 w, const K1U8Params& p,
                                               uint32_t&) {
-    *reinterpret_cast<float4*>(stg + idx) = cvt4(w.x, p);
-    *reinterpret_cast<float4*>(stg + idx + 4) = cvt4(w.y, p);
+    *reinterpret_cast<float4*>(stg + idx) = cvt4(w.x, p, idx);
+    *reinterpret_cast<float4*>(stg + idx + 4) = cvt4(w.y, p, idx + 4);
   }
   static __device__ __forceinline__ void put1(float* stg, int idx, uint32_t v, const K1U8Params& p,
                                               uint32_t&) {
-    stg[idx] = cvt(v, p);
+    stg[idx] = cvt(v, p, idx);
   }
 };
 

@@ -36,6 +36,7 @@ struct K2DgParams {
   const double* rho;
   const double* platt_a;
   const double* platt_b;
+  const unsigned int* tile_ready;  // nullable: [tiles] scans finished by the co-resident projection kernel
   double neg_gamma_fixed;      // -gamma / (feature_scale^2 * 2^32)
   double min_proba;
   float* proba;
@@ -101,14 +102,20 @@ k2_rbf_digits(const __grid_constant__ DgMaps maps, const K2DgParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint64_t pol = policy_evict_last();
-      uint32_t kit = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int ch = 0; ch < p.n_chunks; ++ch) {
-          for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
-            const int s = kit % kDgStages;
-            mbar_wait(&empty[s], ((kit / kDgStages) & 1) ^ 1);
+    const uint64_t pol = policy_evict_last();
+    uint32_t kit = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      if (p.tile_ready) {
+        const int64_t left = p.B - tile * kK2BlockM;
+        const unsigned int need = left < kK2BlockM ? static_cast<unsigned int>(left) : kK2BlockM;
+        while (ld_acquire_gpu(&p.tile_ready[tile]) < need) __nanosleep(200);
+        fence_proxy_async_all();
+      }
+      for (int ch = 0; ch < p.n_chunks; ++ch) {
+        for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
+          const int s = kit % kDgStages;
+          mbar_wait(&empty[s], ((kit / kDgStages) & 1) ^ 1);
+          if (elect_one()) {
             unsigned char* a_dst = smem + s * kDgStageBytes;
             unsigned char* b_dst = a_dst + 3 * kDgABytes;
             mbar_arrive_expect_tx(&full[s], kDgStageBytes);
@@ -119,21 +126,22 @@ k2_rbf_digits(const __grid_constant__ DgMaps maps, const K2DgParams p) {
               tma_load_2d(b_dst + d * kDgBBytes, &maps.b[d], kb * kK2BlockKBytes, ch * kDgTileN, &full[s], pol);
             }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(kCS32, kFmtU8, kFmtU8, kK2BlockM, kDgTileN);
-      uint32_t kit = 0, ait = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int ch = 0; ch < p.n_chunks; ++ch, ++ait) {
-          mbar_wait(tempty, (ait & 1) ^ 1);
+    const uint32_t idesc = umma_idesc(kCS32, kFmtU8, kFmtU8, kK2BlockM, kDgTileN);
+    uint32_t kit = 0, ait = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ch = 0; ch < p.n_chunks; ++ch, ++ait) {
+        mbar_wait(tempty, (ait & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
+          const int s = kit % kDgStages;
+          mbar_wait(&full[s], (kit / kDgStages) & 1);
           tc_fence_after();
-          for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
-            const int s = kit % kDgStages;
-            mbar_wait(&full[s], (kit / kDgStages) & 1);
-            tc_fence_after();
+          if (elect_one()) {
             const uint32_t a_addr = smem_u32(smem + s * kDgStageBytes);
             const uint32_t b_addr = a_addr + 3 * kDgABytes;
 #pragma unroll
@@ -151,8 +159,9 @@ k2_rbf_digits(const __grid_constant__ DgMaps maps, const K2DgParams p) {
               }
             }
             umma_commit(&empty[s]);
+            if (kb == p.k_blocks - 1) umma_commit(tfull);
           }
-          umma_commit(tfull);
+          __syncwarp();
         }
       }
     }
@@ -163,6 +172,11 @@ k2_rbf_digits(const __grid_constant__ DgMaps maps, const K2DgParams p) {
     uint32_t ait = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t b = tile * kK2BlockM + m;
+      if (p.tile_ready) {
+        const int64_t left = p.B - tile * kK2BlockM;
+        const unsigned int need = left < kK2BlockM ? static_cast<unsigned int>(left) : kK2BlockM;
+        while (ld_acquire_gpu(&p.tile_ready[tile]) < need) __nanosleep(200);
+      }
       const long long un = (b < p.B) ? p.unorm[b] : 0;
       double dec[NP];
 #pragma unroll
@@ -218,7 +232,7 @@ k2_rbf_digits(const __grid_constant__ DgMaps maps, const K2DgParams p) {
 }
 
 // (n,F) float32 features scaled like common.process_samples(scale=True) -> three u8 digit planes
-// of X = round(x * scale * 2^16) and the exact 64-bit norms.  Values outside [0, 256/scale) cannot
+// of X = round((x + shift_f) * scale * 2^16) and the exact 64-bit norms.  Values outside [0, 256/scale) cannot
 // be represented: they are clamped and counted in status[2] (RML_E_RANGE).
 struct DgQuantParams {
   const float* feats;
@@ -228,6 +242,7 @@ struct DgQuantParams {
   int64_t B;
   int F, stride;
   double scale;
+  const double* shift;    // nullable [F]: added before scaling (standardised features -> non-negative)
 };
 __global__ void __launch_bounds__(256) k1_quantize_digits(const DgQuantParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,7 +256,8 @@ __global__ void __launch_bounds__(256) k1_quantize_digits(const DgQuantParams p)
   for (int f = lane; f < p.stride; f += 32) {
     uint32_t X = 0;
     if (f < p.F) {
-      const double v = rint(static_cast<double>(x[f]) * p.scale * 65536.0);
+      const double xs = p.shift ? static_cast<double>(x[f]) + p.shift[f] : static_cast<double>(x[f]);
+      const double v = rint(xs * p.scale * 65536.0);
       bad |= !(v >= 0.0 && v < 16777216.0);
       X = static_cast<uint32_t>(fmin(fmax(v, 0.0), 16777215.0));
     }

@@ -213,24 +213,25 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      // the feature tile is re-read once per support-vector chunk: keep it in L2 until then
-      const uint64_t pol_a = p.n_chunks > 1 ? policy_evict_last() : policy_evict_first();
-      const uint64_t pol_b = policy_evict_last();
-      uint32_t kit = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (p.tile_ready) {
-          // fused pipeline: the projection kernel is still running on the other SMs; wait
-          // until every scan of this tile has its feature row in global memory
-          const int64_t left = p.B - tile * kK2BlockM;
-          const unsigned int need = left < kK2BlockM ? static_cast<unsigned int>(left) : kK2BlockM;
-          while (ld_acquire_gpu(&p.tile_ready[tile]) < need) __nanosleep(200);
-          fence_proxy_async_all();
-        }
-        for (int ch = 0; ch < p.n_chunks; ++ch) {
-          for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
-            const int s = kit % kK2Stages;
-            mbar_wait(&empty[s], ((kit / kK2Stages) & 1) ^ 1);
+    // (whole warp in uniform control flow, one elected lane issues: see elect_one())
+    // the feature tile is re-read once per support-vector chunk: keep it in L2 until then
+    const uint64_t pol_a = p.n_chunks > 1 ? policy_evict_last() : policy_evict_first();
+    const uint64_t pol_b = policy_evict_last();
+    uint32_t kit = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      if (p.tile_ready) {
+        // fused pipeline: the projection kernel is still running on the other SMs; wait
+        // until every scan of this tile has its feature row in global memory
+        const int64_t left = p.B - tile * kK2BlockM;
+        const unsigned int need = left < kK2BlockM ? static_cast<unsigned int>(left) : kK2BlockM;
+        while (ld_acquire_gpu(&p.tile_ready[tile]) < need) __nanosleep(200);
+        fence_proxy_async_all();
+      }
+      for (int ch = 0; ch < p.n_chunks; ++ch) {
+        for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
+          const int s = kit % kK2Stages;
+          mbar_wait(&empty[s], ((kit / kK2Stages) & 1) ^ 1);
+          if (elect_one()) {
             unsigned char* a_dst = smem + s * stage_bytes;
             unsigned char* b_dst = a_dst + kK2BlockM * kK2BlockKBytes;
             mbar_arrive_expect_tx(&full[s], stage_bytes);
@@ -238,24 +239,25 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
                         &full[s], pol_a);
             tma_load_2d(b_dst, &map_sv, kb * kK2BlockKBytes, ch * p.n_tile, &full[s], pol_b);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(kCS32, kFmtU8, kFmtU8, kK2BlockM, p.n_tile);
-      uint32_t kit = 0, ait = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int ch = 0; ch < p.n_chunks; ++ch, ++ait) {
-          const int ab = ait & 1;
-          mbar_wait(&tempty[ab], ((ait >> 1) & 1) ^ 1);
+    const uint32_t idesc = umma_idesc(kCS32, kFmtU8, kFmtU8, kK2BlockM, p.n_tile);
+    uint32_t kit = 0, ait = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ch = 0; ch < p.n_chunks; ++ch, ++ait) {
+        const int ab = ait & 1;
+        mbar_wait(&tempty[ab], ((ait >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * kK2MaxTileN;
+        for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
+          const int s = kit % kK2Stages;
+          mbar_wait(&full[s], (kit / kK2Stages) & 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + ab * kK2MaxTileN;
-          for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
-            const int s = kit % kK2Stages;
-            mbar_wait(&full[s], (kit / kK2Stages) & 1);
-            tc_fence_after();
+          if (elect_one()) {
             const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
             const uint32_t b_addr = a_addr + kK2BlockM * kK2BlockKBytes;
             const uint64_t da = umma_desc_k_sw128(a_addr);
@@ -266,8 +268,9 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
               umma_i8(d_tmem, da + (ks * 32 >> 4), db + (ks * 32 >> 4), idesc, (kb | ks) != 0);
             }
             umma_commit(&empty[s]);   // smem stage reusable once these MMAs retire
+            if (kb == p.k_blocks - 1) umma_commit(&tfull[ab]);    // accumulator chunk complete
           }
-          umma_commit(&tfull[ab]);    // accumulator chunk complete
+          __syncwarp();
         }
       }
     }

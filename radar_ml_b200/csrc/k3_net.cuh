@@ -4,7 +4,8 @@
 //                   computed on the host), double accumulation, float32 store — bit-exact.
 //   k4_conv3x3s2    Keras Conv2D(3x3, strides 2, 'same') + folded BatchNorm + ReLU/LeakyReLU
 //                   (dnn.py:45-52, sgan.py:132-154), NHWC, fp32 CUDA-core direct conv
-//                   (round-1 correctness-first version; tensor-core implicit GEMM is next).
+//                   (kept for shapes the implicit GEMM cannot take and for RML_IGEMM=0);
+//   k4_conv_igemm   the same layer for Cin % 64 == 0 as a tcgen05 implicit GEMM (strided 4-D TMA).
 //   k5_dense_stack  Flatten -> Dense 64 -> Dense 64 -> Dense C -> softmax / Z/(Z+1)
 //                   (dnn.py:78-85, sgan.py:185-213).  The K = 38 400 / 24 576 contraction runs
 //                   on tcgen05 (kind::f16, bf16 operands, fp32 accumulate in TMEM, TMA-fed
@@ -506,20 +507,21 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint64_t pol_a = policy_evict_last();    // every activation pixel is read ~2.25 times
-      const uint64_t pol_b = policy_evict_last();
-      uint32_t kit = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t img = tile / p.tiles_per_img;
-        const int tb = static_cast<int>(tile - img * p.tiles_per_img);
-        int oy0 = tb * p.TH;
-        if (oy0 > p.Ho - p.TH) oy0 = p.Ho - p.TH;        // last block overlaps instead of being ragged
-        const int br = static_cast<int>(img % 3);
-        for (int kh = 0; kh < 3; ++kh) {
-          for (int cb = 0; cb < cblocks; ++cb, ++kit) {
-            const int s = kit % n_stages;
-            mbar_wait(&empty[s], ((kit / n_stages) & 1) ^ 1);
+    // whole warp in uniform control flow, one elected lane issues (see elect_one())
+    const uint64_t pol_a = policy_evict_last();    // every activation pixel is read ~2.25 times
+    const uint64_t pol_b = policy_evict_last();
+    uint32_t kit = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t img = tile / p.tiles_per_img;
+      const int tb = static_cast<int>(tile - img * p.tiles_per_img);
+      int oy0 = tb * p.TH;
+      if (oy0 > p.Ho - p.TH) oy0 = p.Ho - p.TH;        // last block overlaps instead of being ragged
+      const int br = static_cast<int>(img % 3);
+      for (int kh = 0; kh < 3; ++kh) {
+        for (int cb = 0; cb < cblocks; ++cb, ++kit) {
+          const int s = kit % n_stages;
+          mbar_wait(&empty[s], ((kit / n_stages) & 1) ^ 1);
+          if (elect_one()) {
             unsigned char* a_dst = smem + s * stage_bytes;
             unsigned char* b_dst = a_dst + kCgTapsPerStage * 128 * 128;
             mbar_arrive_expect_tx(&full[s], kCgTapsPerStage * (a_bytes + w_tile));
@@ -531,22 +533,23 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                           &full[s], pol_b);
             }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(kCF32, kFmtBF16, kFmtBF16, 128, p.Cout);
-      uint32_t kit = 0, ait = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ait) {
-        const int ab = ait & 1;
-        mbar_wait(&tempty[ab], ((ait >> 1) & 1) ^ 1);
+    const uint32_t idesc = umma_idesc(kCF32, kFmtBF16, kFmtBF16, 128, p.Cout);
+    uint32_t kit = 0, ait = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ait) {
+      const int ab = ait & 1;
+      mbar_wait(&tempty[ab], ((ait >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + ab * 128;
+      for (int kb = 0; kb < k_stages; ++kb, ++kit) {
+        const int s = kit % n_stages;
+        mbar_wait(&full[s], (kit / n_stages) & 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + ab * 128;
-        for (int kb = 0; kb < k_stages; ++kb, ++kit) {
-          const int s = kit % n_stages;
-          mbar_wait(&full[s], (kit / n_stages) & 1);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           const uint32_t b_addr = a_addr + kCgTapsPerStage * 128 * 128;
 #pragma unroll
@@ -558,8 +561,9 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
               umma_f16(d_tmem, da + (ks * 32 >> 4), db + (ks * 32 >> 4), idesc, (kb | kw | ks) != 0);
           }
           umma_commit(&empty[s]);
+          if (kb == k_stages - 1) umma_commit(&tfull[ab]);
         }
-        umma_commit(&tfull[ab]);
+        __syncwarp();
       }
     }
   } else {
@@ -696,14 +700,15 @@ k5_dense_stack(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   const int k_steps = p.k_blocks / kpg;
   constexpr int kABytes = kK5BlockM * kK5BlockK * 2, kBBytes = kK5N * kK5BlockK * 2;
   if (warp == 0) {
-    if (lane == 0) {
-      const uint64_t pol_a = policy_evict_first();
-      const uint64_t pol_b = policy_evict_last();
-      uint32_t kit = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int ks = 0; ks < k_steps; ++ks, ++kit) {
-          const int s = kit % n_st;
-          mbar_wait(&empty[s], ((kit / n_st) & 1) ^ 1);
+    // whole warp in uniform control flow, one elected lane issues (see elect_one())
+    const uint64_t pol_a = policy_evict_first();
+    const uint64_t pol_b = policy_evict_last();
+    uint32_t kit = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ks = 0; ks < k_steps; ++ks, ++kit) {
+        const int s = kit % n_st;
+        mbar_wait(&empty[s], ((kit / n_st) & 1) ^ 1);
+        if (elect_one()) {
           unsigned char* a_dst = smem + s * st_bytes;
           unsigned char* b_dst = a_dst + kpg * kABytes;
           mbar_arrive_expect_tx(&full[s], st_bytes);
@@ -714,21 +719,22 @@ k5_dense_stack(const __grid_constant__ CUtensorMap map_act, const __grid_constan
             tma_load_2d(b_dst + g * kBBytes, &map_w1, kb * kK5BlockK, 0, &full[s], pol_b);
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(kCF32, kFmtBF16, kFmtBF16, kK5BlockM, kK5N);
-      uint32_t kit = 0, ait = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ait) {
-        const int ab = ait & 1;
-        mbar_wait(&tempty[ab], ((ait >> 1) & 1) ^ 1);
+    const uint32_t idesc = umma_idesc(kCF32, kFmtBF16, kFmtBF16, kK5BlockM, kK5N);
+    uint32_t kit = 0, ait = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ait) {
+      const int ab = ait & 1;
+      mbar_wait(&tempty[ab], ((ait >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + ab * kK5N;
+      for (int ks = 0; ks < k_steps; ++ks, ++kit) {
+        const int s = kit % n_st;
+        mbar_wait(&full[s], (kit / n_st) & 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + ab * kK5N;
-        for (int ks = 0; ks < k_steps; ++ks, ++kit) {
-          const int s = kit % n_st;
-          mbar_wait(&full[s], (kit / n_st) & 1);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * st_bytes);
           const uint32_t b_addr = a_addr + kpg * kABytes;
           for (int g = 0; g < kpg; ++g) {
@@ -739,8 +745,9 @@ k5_dense_stack(const __grid_constant__ CUtensorMap map_act, const __grid_constan
               umma_f16(d_tmem, da + (k16 * 32 >> 4), db + (k16 * 32 >> 4), idesc, (ks | g | k16) != 0);
           }
           umma_commit(&empty[s]);
+          if (ks == k_steps - 1) umma_commit(&tfull[ab]);
         }
-        umma_commit(&tfull[ab]);
+        __syncwarp();
       }
     }
   } else {

@@ -10,6 +10,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// One lane of a fully converged warp.  The single-thread roles (TMA producer, tcgen05.mma issuer)
+// walk their loops with the WHOLE warp in uniform control flow and wrap only the issue in
+// `if (elect_one())`: under a plain `if (lane == 0)` the compiler cannot prove the descriptor /
+// address operands warp-uniform and wraps every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST +
+// BRA.U.ANY waterfall loop — measured 65 cycles of issue per tcgen05.mma (tools/umma_probe.cu),
+// above the tensor floor of every N <= 128 tile.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+  return pred != 0;
+}
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
@@ -52,6 +54,9 @@ struct Model {
   double* pairw_dg = nullptr;     // [NP][dg_pad]
   int dg_pad = 0, dg_chunks = 0;
   CUtensorMap map_sv_dg[3];
+  double dg_scale = 255.0;        // fixed-point scale of the digit planes: X = round((x + shift_f) * dg_scale * 2^16)
+  double* dg_shift = nullptr;     // device [F] shift_f (null: 0) — per-feature affine loaded before the model
+  int i8_stages = 0;              // ring depth of k2_rbf_i8 for this model
 };
 
 constexpr int kHostBufs = 3;
@@ -67,6 +72,38 @@ struct HostPipe {
   cudaStream_t stream[kHostBufs] = {nullptr};
   size_t work_bytes = 0;
 };
+
+// scratch of the small host-buffer calls (rml_score_host / rml_predict_targets_host): one scan's
+// cube, T <= kSmallMax feature rows and their results, plus pinned mirrors of the results
+constexpr int64_t kSmallMax = 1024;
+struct SmallPipe {
+  int64_t cap = 0;            // rows
+  int F = 0;
+  void* cube = nullptr;       // one cube (float32)
+  int32_t* ijk = nullptr;
+  float* feats = nullptr;     // [cap][F] f32
+  void* work = nullptr;       // predict workspace for cap rows
+  size_t work_bytes = 0;
+  float* proba = nullptr;
+  int32_t* label = nullptr;
+  uint8_t* known = nullptr;
+  unsigned char* pinned = nullptr;   // host: proba | label | known | status(16)
+  size_t pinned_bytes = 0;
+};
+
+// NCCL through dlopen (the torch-bundled libnccl.so.2 or the system one): the library must not
+// link against a particular NCCL build, and a process that never calls rml_comm_init needs none.
+typedef struct { char internal[128]; } rml_nccl_uid;
+struct Nccl {
+  void* handle = nullptr;
+  int (*GetUniqueId)(rml_nccl_uid*) = nullptr;
+  int (*CommInitRank)(void**, int, rml_nccl_uid, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+Nccl g_nccl;
+
 
 struct NetConv {
   int cin = 0, cout = 0, act = 0;
@@ -104,6 +141,15 @@ struct rml_ctx {
   double r_min = 10, r_max = 360, th_min = -42, th_max = 42, ph_min = -30, ph_max = 30;
   float aff_offset = 0.f, aff_scale = 255.f;
   int aff_enabled = 1;
+  float* aff_off_dev = nullptr;   // per-feature tables of rml_load_affine (null: scalar pair above)
+  float* aff_scl_dev = nullptr;
+  int aff_F = 0;
+  std::vector<double> aff_shift;  // offset[f] / scale[f]: makes standardised features non-negative (digit path)
+  int k1_split = 1, k5_kpg = 0;   // tuning experiments (RML_K1_SPLIT, RML_K5_KPG), read once at create
+  int force_f32 = 0;              // rml_set_precision: 1 = float32 features even for an integral model
+  void* nccl_comm = nullptr;
+  int nccl_rank = 0, nccl_world = 1;
+  SmallPipe small;
   Model model;
   unsigned int* status = nullptr;  // [0] non-integral values, [1] slice index errors
   int64_t launches = 0;
@@ -125,7 +171,8 @@ struct rml_ctx {
   int64_t fused_min_b = 8192;
   int fused_enabled = 1;     // RML_FUSED=0 disables
   int last_fused = 0;
-  // scratch of the multi-digit scorer (grow-only)
+  // scratch of the multi-digit scorer for stand-alone rml_score calls (sized by rml_reserve;
+  // rml_predict takes its digit planes from the caller's workspace)
   uint8_t* dg_planes = nullptr;
   long long* dg_norms = nullptr;
   int64_t dg_cap = 0;
@@ -193,6 +240,7 @@ void free_model(Model& m) {
   cudaFree(m.rho);
   cudaFree(m.platt_a);
   cudaFree(m.platt_b);
+  cudaFree(m.dg_shift);
   m = Model();
 }
 
@@ -222,9 +270,8 @@ template <int C>
 int launch_rbf_i8(rml_ctx* c, const CUtensorMap& map_feats, const K2Params& p, cudaStream_t st,
                   int grid_limit) {
   const int smem = k2_smem_bytes(p.n_tile, p.stages, p.n_pad, C * (C - 1) / 2);
-  if (p.stages < 2)
+  if (p.stages < 2)   // rml_load_svc_rbf routes such models to the digit / general scorer
     return fail(c, RML_E_UNSUPPORTED, "k2_rbf_i8: %d support vectors x %d classes do not leave room for a 2-stage pipeline", p.n_sv, C);
-  RML_CUDA(c, cudaFuncSetAttribute(k2_rbf_i8<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int64_t tiles = (p.B + kK2BlockM - 1) / kK2BlockM;
   const int sms = grid_limit > 0 ? grid_limit : c->num_sms;
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
@@ -234,11 +281,11 @@ int launch_rbf_i8(rml_ctx* c, const CUtensorMap& map_feats, const K2Params& p, c
   return RML_OK;
 }
 template <int C>
-int launch_rbf_digits(rml_ctx* c, const DgMaps& maps, const K2DgParams& p, cudaStream_t st) {
+int launch_rbf_digits(rml_ctx* c, const DgMaps& maps, const K2DgParams& p, cudaStream_t st, int grid_limit = 0) {
   const int smem = k2dg_smem_bytes(p.n_pad, C * (C - 1) / 2);
-  RML_CUDA(c, cudaFuncSetAttribute(k2_rbf_digits<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int64_t tiles = (p.B + kK2BlockM - 1) / kK2BlockM;
-  const int grid = static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
+  const int sms = grid_limit > 0 ? grid_limit : c->num_sms;
+  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
   k2_rbf_digits<C><<<grid, kK2Threads, smem, st>>>(maps, p);
   RML_CUDA(c, cudaGetLastError());
   ++c->launches;
@@ -274,21 +321,51 @@ int launch_linear(rml_ctx* c, const K2LinParams& p, cudaStream_t st) {
 struct Affine {
   float offset, scale;
   int enabled;
+  const float* off_tab = nullptr;   // per-feature tables (device), replace the scalar pair
+  const float* scl_tab = nullptr;
 };
+
+// every kernel that needs more than 48 KB of dynamic shared memory opts in ONCE, at rml_create
+template <typename K>
+cudaError_t opt_in_smem(K kernel) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+}
+int set_kernel_attributes(rml_ctx* c) {
+  RML_CUDA(c, opt_in_smem(k1_project_max<uint8_t>));
+  RML_CUDA(c, opt_in_smem(k1_project_max<float>));
+  RML_CUDA(c, opt_in_smem(k1_project_max_u8in<uint8_t>));
+  RML_CUDA(c, opt_in_smem(k1_project_max_u8in<float>));
+  RML_CUDA(c, opt_in_smem(k2_rbf_i8<2>)); RML_CUDA(c, opt_in_smem(k2_rbf_i8<3>)); RML_CUDA(c, opt_in_smem(k2_rbf_i8<4>));
+  RML_CUDA(c, opt_in_smem(k2_rbf_i8<5>)); RML_CUDA(c, opt_in_smem(k2_rbf_i8<6>));
+  RML_CUDA(c, opt_in_smem(k2_rbf_digits<2>)); RML_CUDA(c, opt_in_smem(k2_rbf_digits<3>)); RML_CUDA(c, opt_in_smem(k2_rbf_digits<4>));
+  RML_CUDA(c, opt_in_smem(k2_rbf_digits<5>)); RML_CUDA(c, opt_in_smem(k2_rbf_digits<6>));
+  RML_CUDA(c, opt_in_smem(k0_derive_targets));
+  RML_CUDA(c, opt_in_smem(k0_zoom_concat));
+  RML_CUDA(c, opt_in_smem(k3_resize_pil));
+  RML_CUDA(c, opt_in_smem(k34_resize_conv1<2>));
+  RML_CUDA(c, opt_in_smem(k34_resize_conv1<4>));
+  RML_CUDA(c, opt_in_smem(k4_conv3x3s2));
+  RML_CUDA(c, opt_in_smem(k4_conv_igemm));
+  RML_CUDA(c, opt_in_smem(k5_dense_stack));
+  return RML_OK;
+}
 
 // cubes: float32 voxels (predict.py:91) or, with cube_u8 != 0, the sensor's integers as uint8
 int project_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32_t* ijk,
                  uint32_t mask, int dtype, void* feats, int32_t* norms, cudaStream_t st,
                  int grid_limit = 0, unsigned int* tile_done = nullptr, const Affine* aff_in = nullptr,
-                 int cube_u8 = 0) {
-  const Affine aff = aff_in ? *aff_in : Affine{c->aff_offset, c->aff_scale, c->aff_enabled};
+                 int cube_u8 = 0, int64_t cube_stride = -1) {
+  const Affine aff = aff_in ? *aff_in : Affine{c->aff_offset, c->aff_scale, c->aff_enabled, c->aff_off_dev, c->aff_scl_dev};
   if (B < 0 || !cubes || !feats) return fail(c, RML_E_INVALID, "rml_project: null buffer or B<0");
+  if (aff.off_tab && aff.enabled && dtype == RML_F32 && c->aff_F != feature_len(c, mask))
+    return fail(c, RML_E_INVALID, "rml_project: the per-feature affine has F=%d, mask %u gives F=%d",
+                c->aff_F, mask, feature_len(c, mask));
   if ((mask & RML_MASK_ALL) == 0 || (mask & ~RML_MASK_ALL))
     return fail(c, RML_E_INVALID, "rml_project: mask %u selects no projection", mask);
   if (mode != RML_MODE_MAX && mode != RML_MODE_SLICE) return fail(c, RML_E_INVALID, "bad mode %d", mode);
   if (mode == RML_MODE_SLICE && !ijk) return fail(c, RML_E_INVALID, "SLICE mode needs ijk");
   if (dtype != RML_F32 && dtype != RML_U8) return fail(c, RML_E_INVALID, "bad dtype %d", dtype);
-  const bool fast = mode == RML_MODE_MAX && c->sx == kSX && c->sy == kSY && c->sz == kSZ;
+  const bool fast = mode == RML_MODE_MAX && c->sx == kSX && c->sy == kSY && c->sz == kSZ && cube_stride < 0;
   // bulk copies / float4 loads need 16-byte granules; uint8 cubes outside the streaming kernel
   // are read as uchar4 at most
   const uintptr_t cube_align = (cube_u8 && !fast) ? 3 : 15;
@@ -302,6 +379,7 @@ int project_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32
     p.cubes = static_cast<const uint8_t*>(cubes); p.feats = feats; p.norms = norms; p.B = B;
     p.stride = stride; p.F = F; p.mask = mask;
     p.offset = aff.offset; p.scale = aff.scale; p.affine = aff.enabled;
+    p.aff_off = aff.off_tab; p.aff_scl = aff.scl_tab;
     p.tile_done = dtype == RML_U8 ? tile_done : nullptr;
     const int sms = grid_limit > 0 ? grid_limit : c->num_sms;
     const int64_t ctas = static_cast<int64_t>(sms) *
@@ -309,11 +387,9 @@ int project_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32
     const int grid = static_cast<int>(B < ctas ? B : ctas);
     if (dtype == RML_U8) {
       const int smem = k1u8_smem_bytes<uint8_t>();
-      RML_CUDA(c, cudaFuncSetAttribute(k1_project_max_u8in<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       k1_project_max_u8in<uint8_t><<<grid, kK1Threads, smem, st>>>(p);
     } else {
       const int smem = k1u8_smem_bytes<float>();
-      RML_CUDA(c, cudaFuncSetAttribute(k1_project_max_u8in<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       k1_project_max_u8in<float><<<grid, kK1Threads, smem, st>>>(p);
     }
   } else if (fast) {
@@ -321,18 +397,16 @@ int project_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32
     p.cubes = static_cast<const float*>(cubes); p.feats = feats; p.norms = norms; p.status = c->status; p.B = B;
     p.stride = stride; p.F = F; p.mask = mask;
     p.offset = aff.offset; p.scale = aff.scale; p.affine = aff.enabled;
+    p.aff_off = aff.off_tab; p.aff_scl = aff.scl_tab;
     p.tile_done = dtype == RML_U8 ? tile_done : nullptr;
-    p.split = 1;
-    if (const char* e = getenv("RML_K1_SPLIT")) { const int v = atoi(e); if (v == 2 || v == 4) p.split = v; }
+    p.split = c->k1_split;
     const int sms = grid_limit > 0 ? grid_limit : c->num_sms;
     const int grid = static_cast<int>(B < sms ? B : sms);
     if (dtype == RML_U8) {
       const int smem = k1_smem_bytes<uint8_t>();
-      RML_CUDA(c, cudaFuncSetAttribute(k1_project_max<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       k1_project_max<uint8_t><<<grid, kK1Threads, smem, st>>>(p);
     } else {
       const int smem = k1_smem_bytes<float>();
-      RML_CUDA(c, cudaFuncSetAttribute(k1_project_max<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       k1_project_max<float><<<grid, kK1Threads, smem, st>>>(p);
     }
   } else {
@@ -340,6 +414,8 @@ int project_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32
     p.cubes = cubes; p.ijk = ijk; p.feats = feats; p.norms = norms; p.status = c->status; p.B = B;
     p.sx = c->sx; p.sy = c->sy; p.sz = c->sz; p.stride = stride; p.F = F; p.mask = mask;
     p.offset = aff.offset; p.scale = aff.scale; p.affine = aff.enabled; p.mode = mode;
+    p.aff_off = aff.off_tab; p.aff_scl = aff.scl_tab;
+    p.cube_stride = cube_stride >= 0 ? cube_stride : static_cast<int64_t>(c->sx) * c->sy * c->sz;
     const int64_t want = B < 8ll * c->num_sms ? B : 8ll * c->num_sms;
     const int grid = static_cast<int>(want);
     const bool vec_slice = mode == RML_MODE_SLICE && (c->sz & 3) == 0 && (dtype != RML_U8 || (stride & 3) == 0);
@@ -366,9 +442,19 @@ int project_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32
   return RML_OK;
 }
 
+inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+// scratch the multi-digit scorer needs for B float32 feature rows: 3 digit planes + 64-bit norms
+size_t digit_scratch_bytes(const rml_ctx* c, int64_t B) {
+  const Model& m = c->model;
+  if (m.kind != 1 || !m.digits_ok || B <= 0) return 0;
+  return align256(static_cast<size_t>(3) * B * m.kpad) + align256(static_cast<size_t>(B) * 8);
+}
+
 int score_impl(rml_ctx* c, const void* feats, int dtype, const int32_t* norms, int64_t B,
                double min_proba, float* proba, float* decision, int32_t* label, uint8_t* known,
-               cudaStream_t st, int grid_limit = 0, const unsigned int* tile_ready = nullptr) {
+               cudaStream_t st, int grid_limit = 0, const unsigned int* tile_ready = nullptr,
+               void* dg_scratch = nullptr, bool planes_ready = false) {
   Model& m = c->model;
   if (m.kind == 0) return fail(c, RML_E_NOMODEL, "rml_score: no model loaded");
   if (!feats || !proba || !label || B < 0) return fail(c, RML_E_INVALID, "rml_score: null buffer or B<0");
@@ -396,7 +482,7 @@ int score_impl(rml_ctx* c, const void* feats, int dtype, const int32_t* norms, i
     K2Params p;
     p.B = B; p.n_sv = m.n_sv; p.n_tile = m.n_tile; p.n_chunks = m.n_chunks; p.k_blocks = m.kpad / 128;
     p.n_pad = m.n_tile * m.n_chunks;
-    p.stages = k2_pick_stages(m.n_tile, p.n_pad, m.C * (m.C - 1) / 2);
+    p.stages = m.i8_stages;
     p.unorm = norms; p.svnorm = m.svnorm; p.pairw = m.pairw; p.rho = m.rho;
     p.platt_a = m.platt_a; p.platt_b = m.platt_b;
     p.neg_gamma_s2 = -m.gamma / (m.feature_scale * m.feature_scale);
@@ -405,35 +491,47 @@ int score_impl(rml_ctx* c, const void* feats, int dtype, const int32_t* norms, i
     DISPATCH_C(m.C, launch_rbf_i8<CC>(c, map_feats, p, st, grid_limit));
   }
   if (dtype == RML_F32 && m.digits_ok) {
-    // tensor-core exact path: float32 features -> 24-bit fixed point digit planes -> 9 u8 GEMMs
+    // tensor-core exact path: float32 features -> 24-bit fixed point digit planes -> 9 u8 GEMMs.
+    // The planes live in caller-provided scratch (rml_predict's workspace) or in the context
+    // scratch sized by rml_reserve; nothing is allocated here.
     if (reinterpret_cast<uintptr_t>(feats) & 3) return fail(c, RML_E_INVALID, "feats must be 4-byte aligned");
-    if (c->dg_cap < B) {
-      cudaFree(c->dg_planes); cudaFree(c->dg_norms);
-      c->dg_planes = nullptr; c->dg_norms = nullptr; c->dg_cap = 0;
-      RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->dg_planes), static_cast<size_t>(3) * B * m.kpad));
-      RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->dg_norms), static_cast<size_t>(B) * 8));
-      c->dg_cap = B;
+    uint8_t* planes;
+    long long* dnorms;
+    if (dg_scratch) {
+      planes = static_cast<uint8_t*>(dg_scratch);
+      dnorms = reinterpret_cast<long long*>(planes + align256(static_cast<size_t>(3) * B * m.kpad));
+    } else {
+      if (c->dg_cap < B)
+        return fail(c, RML_E_INVALID, "rml_score: float32 features of this model need %lld rows of digit scratch, "
+                    "%lld reserved; call rml_reserve(ctx, max_batch, RML_RESERVE_SCORE) first",
+                    static_cast<long long>(B), static_cast<long long>(c->dg_cap));
+      planes = c->dg_planes;
+      dnorms = c->dg_norms;
     }
-    DgQuantParams qp;
-    qp.feats = static_cast<const float*>(feats); qp.planes = c->dg_planes; qp.norms = c->dg_norms;
-    qp.status = c->status; qp.B = B; qp.F = m.F; qp.stride = m.kpad; qp.scale = m.feature_scale;
-    k1_quantize_digits<<<static_cast<unsigned>((B + 7) / 8), 256, 0, st>>>(qp);
-    RML_CUDA(c, cudaGetLastError());
-    ++c->launches;
+    if (!planes_ready) {
+      DgQuantParams qp;
+      qp.feats = static_cast<const float*>(feats); qp.planes = planes; qp.norms = dnorms;
+      qp.status = c->status; qp.B = B; qp.F = m.F; qp.stride = m.kpad; qp.scale = m.dg_scale;
+      qp.shift = m.dg_shift;
+      k1_quantize_digits<<<static_cast<unsigned>((B + 7) / 8), 256, 0, st>>>(qp);
+      RML_CUDA(c, cudaGetLastError());
+      ++c->launches;
+    }
     DgMaps maps;
     const size_t plane = static_cast<size_t>(B) * m.kpad;
     for (int d = 0; d < 3; ++d) {
-      int rc = encode_u8_map(c, &maps.a[d], c->dg_planes + d * plane, B, m.F, m.kpad, kK2BlockM);
+      int rc = encode_u8_map(c, &maps.a[d], planes + d * plane, B, m.F, m.kpad, kK2BlockM);
       if (rc) return rc;
       maps.b[d] = m.map_sv_dg[d];
     }
     K2DgParams dp;
     dp.B = B; dp.n_sv = m.n_sv; dp.n_chunks = m.dg_chunks; dp.k_blocks = m.kpad / 128; dp.n_pad = m.dg_pad;
-    dp.unorm = c->dg_norms; dp.svnorm = m.svnorm64; dp.pairw = m.pairw_dg; dp.rho = m.rho;
+    dp.unorm = dnorms; dp.svnorm = m.svnorm64; dp.pairw = m.pairw_dg; dp.rho = m.rho;
     dp.platt_a = m.platt_a; dp.platt_b = m.platt_b;
-    dp.neg_gamma_fixed = -m.gamma / (m.feature_scale * m.feature_scale * 4294967296.0);
+    dp.tile_ready = tile_ready;
+    dp.neg_gamma_fixed = -m.gamma / (m.dg_scale * m.dg_scale * 4294967296.0);
     dp.min_proba = min_proba; dp.proba = proba; dp.decision = decision; dp.label = label; dp.known = known;
-    DISPATCH_C(m.C, launch_rbf_digits<CC>(c, maps, dp, st));
+    DISPATCH_C(m.C, launch_rbf_digits<CC>(c, maps, dp, st, grid_limit));
   }
   K2GenParams p;
   p.B = B; p.F = m.F; p.n_sv = m.n_sv; p.feats = static_cast<const float*>(feats); p.sv = m.sv_f64;
@@ -444,59 +542,73 @@ int score_impl(rml_ctx* c, const void* feats, int dtype, const int32_t* norms, i
   DISPATCH_C(m.C, launch_rbf_general<CC>(c, p, st));
 }
 
-inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
-
+// u8 operand rows + the integer tensor-core scorer: an integral SVC (or a linear model, whose
+// scorer reads either row type) AND no per-feature affine AND not overridden by rml_set_precision
 bool use_u8_path(const rml_ctx* c) {
+  if (c->force_f32 || c->aff_off_dev) return false;
   return c->model.kind == 2 || (c->model.kind == 1 && c->model.integral);
+}
+
+// Workspace plan of rml_predict for B scans (everything the call needs; nothing is allocated):
+//   [feature rows][norms int32][digit planes + 64-bit norms (float32 path of an SVC)][tile counters]
+struct PredictPlan {
+  int dtype;
+  size_t feat_bytes, norm_off, dg_off, tile_off, total;
+};
+PredictPlan predict_plan(const rml_ctx* c, int64_t B, uint32_t mask) {
+  PredictPlan pl;
+  pl.dtype = use_u8_path(c) ? RML_U8 : RML_F32;
+  const size_t stride = feature_stride(c, mask, pl.dtype);
+  pl.feat_bytes = align256(static_cast<size_t>(B) * stride * (pl.dtype == RML_U8 ? 1 : 4));
+  pl.norm_off = pl.feat_bytes;
+  pl.dg_off = pl.norm_off + align256(static_cast<size_t>(B) * 4);
+  pl.tile_off = pl.dg_off + (pl.dtype == RML_F32 ? digit_scratch_bytes(c, B) : 0);
+  pl.total = pl.tile_off + align256(static_cast<size_t>((B + kK2BlockM - 1) / kK2BlockM) * 4) + 256;
+  return pl;
 }
 
 int predict_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32_t* ijk,
                  uint32_t mask, double min_proba, void* work, float* proba, int32_t* label,
-                 uint8_t* known, cudaStream_t st, int cube_u8 = 0) {
+                 uint8_t* known, cudaStream_t st, int cube_u8 = 0, int64_t cube_stride = -1) {
   if (c->model.kind == 0) return fail(c, RML_E_NOMODEL, "rml_predict: no model loaded");
   if (feature_len(c, mask) != c->model.F)
     return fail(c, RML_E_INVALID, "rml_predict: mask gives F=%d but the model has F=%d",
                 feature_len(c, mask), c->model.F);
   if (!work) return fail(c, RML_E_INVALID, "rml_predict: workspace is null");
-  const int dtype = use_u8_path(c) ? RML_U8 : RML_F32;
-  const size_t stride = feature_stride(c, mask, dtype);
-  const size_t feat_bytes = align256(static_cast<size_t>(B) * stride * (dtype == RML_U8 ? 1 : 4));
-  int32_t* norms = reinterpret_cast<int32_t*>(static_cast<char*>(work) + feat_bytes);
-  // the scorer expects features scaled like common.process_samples(scale=True)
-  const Affine aff{0.f, static_cast<float>(c->model.feature_scale), 1};
+  if (reinterpret_cast<uintptr_t>(work) & 255) return fail(c, RML_E_INVALID, "rml_predict: workspace must be 256-byte aligned");
+  const PredictPlan pl = predict_plan(c, B, mask);
+  const int dtype = pl.dtype;
+  char* ws = static_cast<char*>(work);
+  int32_t* norms = reinterpret_cast<int32_t*>(ws + pl.norm_off);
+  void* dg_scratch = (dtype == RML_F32 && c->model.kind == 1 && c->model.digits_ok) ? ws + pl.dg_off : nullptr;
+  unsigned int* tile_done = reinterpret_cast<unsigned int*>(ws + pl.tile_off);
+  // the scorer expects features scaled like common.process_samples(scale=True) — or, with a
+  // per-feature affine loaded, standardised like the scaler the model was trained behind
+  const Affine aff = c->aff_off_dev ? Affine{0.f, 1.f, 1, c->aff_off_dev, c->aff_scl_dev}
+                                    : Affine{0.f, static_cast<float>(c->model.feature_scale), 1};
   // uint8 cubes stream 4x faster, so the scorer gets a larger share of the SMs
   const int k2_sms = cube_u8 ? c->k2_sms_u8 : c->k2_sms;
   const bool fused = c->fused_enabled && c->model.kind == 1 && dtype == RML_U8 && mode == RML_MODE_MAX &&
                      c->sx == kSX && c->sy == kSY && c->sz == kSZ && B >= c->fused_min_b &&
-                     k2_sms > 0 && k2_sms < c->num_sms;
+                     k2_sms > 0 && k2_sms < c->num_sms && cube_stride < 0;
   c->last_fused = fused ? 1 : 0;
   if (fused) {
     // One pipeline, two co-resident kernels: K1 streams cubes on (num_sms - k2_sms) SMs and
     // bumps a per-tile counter for every finished scan; K2 runs on the remaining SMs and
     // starts on a 128-scan tile as soon as its counter is full (device-side flags, no host sync).
     const int64_t tiles = (B + kK2BlockM - 1) / kK2BlockM;
-    if (!c->aux_stream) {
-      RML_CUDA(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
-      RML_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-      RML_CUDA(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    }
-    if (c->tile_done_cap < tiles) {
-      cudaFree(c->tile_done);
-      RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->tile_done), tiles * sizeof(unsigned int)));
-      c->tile_done_cap = tiles;
-    }
-    // a previous fused call (possibly on another stream) may still be reading the counters
+    // a previous fused call (possibly on another stream) may still be reading its counters
     RML_CUDA(c, cudaStreamWaitEvent(st, c->ev_join, 0));
-    RML_CUDA(c, cudaMemsetAsync(c->tile_done, 0, tiles * sizeof(unsigned int), st));
+    RML_CUDA(c, cudaMemsetAsync(tile_done, 0, tiles * sizeof(unsigned int), st));
     RML_CUDA(c, cudaEventRecord(c->ev_fork, st));
     RML_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
     if (c->ev_k1a) RML_CUDA(c, cudaEventRecord(c->ev_k1a, st));
     int rc = project_impl(c, cubes, B, mode, ijk, mask, dtype, work, norms, st,
-                          c->num_sms - k2_sms, c->tile_done, &aff, cube_u8);
+                          c->num_sms - k2_sms, tile_done, &aff, cube_u8);
     if (c->ev_k1b) RML_CUDA(c, cudaEventRecord(c->ev_k1b, st));
     if (rc) return rc;
     rc = score_impl(c, work, dtype, norms, B, min_proba, proba, nullptr, label, known, c->aux_stream,
-                    k2_sms, c->tile_done);
+                    k2_sms, tile_done);
     if (rc) return rc;
     RML_CUDA(c, cudaEventRecord(c->ev_join, c->aux_stream));
     RML_CUDA(c, cudaStreamWaitEvent(st, c->ev_join, 0));
@@ -504,10 +616,11 @@ int predict_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32
     return RML_OK;
   }
   if (c->ev_k1a) RML_CUDA(c, cudaEventRecord(c->ev_k1a, st));
-  int rc = project_impl(c, cubes, B, mode, ijk, mask, dtype, work, norms, st, 0, nullptr, &aff, cube_u8);
+  int rc = project_impl(c, cubes, B, mode, ijk, mask, dtype, work, norms, st, 0, nullptr, &aff, cube_u8,
+                        cube_stride);
   if (c->ev_k1b) RML_CUDA(c, cudaEventRecord(c->ev_k1b, st));
   if (rc) return rc;
-  rc = score_impl(c, work, dtype, norms, B, min_proba, proba, nullptr, label, known, st);
+  rc = score_impl(c, work, dtype, norms, B, min_proba, proba, nullptr, label, known, st, 0, nullptr, dg_scratch);
   if (c->ev_k2b && rc == RML_OK) RML_CUDA(c, cudaEventRecord(c->ev_k2b, st));
   return rc;
 }
@@ -520,6 +633,13 @@ void free_net(Net& n) {
   cudaFree(n.w1t); cudaFree(n.b1); cudaFree(n.w2); cudaFree(n.b2); cudaFree(n.w3); cudaFree(n.b3);
   for (int b = 0; b < 3; ++b) { cudaFree(n.kh[b]); cudaFree(n.kv[b]); cudaFree(n.bh[b]); cudaFree(n.bv[b]); }
   n = Net();
+}
+
+void free_small(SmallPipe& sp) {
+  cudaFree(sp.cube); cudaFree(sp.ijk); cudaFree(sp.feats); cudaFree(sp.work);
+  cudaFree(sp.proba); cudaFree(sp.label); cudaFree(sp.known);
+  if (sp.pinned) cudaFreeHost(sp.pinned);
+  sp = SmallPipe();
 }
 
 void free_pipe(HostPipe& hp) {
@@ -574,6 +694,19 @@ int rml_create(int device, rml_ctx** out) {
     delete c;
     return fail(nullptr, RML_E_CUDA, "status allocation failed");
   }
+  // everything a hot entry point would otherwise create lazily: kernel attributes, the second
+  // stream of the co-resident pipeline and its events
+  if (set_kernel_attributes(c) != RML_OK ||
+      cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    g_create_error = "rml_create: kernel attribute / stream setup failed: " + c->err;
+    cudaFree(c->status);
+    delete c;
+    return RML_E_CUDA;
+  }
+  if (const char* e6 = getenv("RML_K1_SPLIT")) { const int v = atoi(e6); if (v == 2 || v == 4) c->k1_split = v; }
+  if (const char* e7 = getenv("RML_K5_KPG")) { const int v = atoi(e7); if (v == 1 || v == 2 || v == 4) c->k5_kpg = v; }
   // measured optimum on B200 (148 SMs): 32 scorer SMs, 116 projection SMs (profiles/r1_fused_sweep.txt)
   c->k2_sms = (c->num_sms * 32 + 74) / 148;
   if (const char* e1 = getenv("RML_K2_SMS")) c->k2_sms = atoi(e1);
@@ -597,6 +730,10 @@ int rml_destroy(rml_ctx* c) {
   cudaFree(c->tile_done);
   cudaFree(c->dg_planes);
   cudaFree(c->dg_norms);
+  cudaFree(c->aff_off_dev);
+  cudaFree(c->aff_scl_dev);
+  free_small(c->small);
+  if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
   free_net(c->net);
   for (int q = 0; q < 3; ++q) { cudaFree(c->zoom_ar[q]); cudaFree(c->zoom_ac[q]); }
   cudaFree(c->status);
@@ -624,7 +761,44 @@ int rml_feature_stride(const rml_ctx* c, uint32_t mask, int dtype) {
 int rml_set_affine(rml_ctx* c, float offset, float scale, int enabled) {
   if (!c) return RML_E_INVALID;
   if (enabled && scale == 0.f) return fail(c, RML_E_INVALID, "affine scale must be non-zero");
+  if (c->aff_off_dev)
+    return fail(c, RML_E_INVALID, "rml_set_affine: a per-feature affine is loaded; clear it with rml_load_affine(ctx, NULL, NULL, 0) first");
   c->aff_offset = offset; c->aff_scale = scale; c->aff_enabled = enabled;
+  return RML_OK;
+}
+
+int rml_load_affine(rml_ctx* c, const float* offset, const float* scale, int F) {
+  if (!c) return RML_E_INVALID;
+  DeviceGuard g(c->device);
+  cudaDeviceSynchronize();
+  cudaFree(c->aff_off_dev); cudaFree(c->aff_scl_dev);
+  c->aff_off_dev = c->aff_scl_dev = nullptr;
+  c->aff_F = 0;
+  c->aff_shift.clear();
+  // a model digitised under another affine no longer matches its features: it keeps working
+  // through the float64 scorer until it is loaded again
+  if (c->model.kind == 1) c->model.digits_ok = false;
+  if (!offset && !scale) {           // back to the reference default, common.py:148
+    c->aff_offset = 0.f; c->aff_scale = 255.f; c->aff_enabled = 1;
+    return RML_OK;
+  }
+  if (!offset || !scale || F <= 0) return fail(c, RML_E_INVALID, "rml_load_affine: offset and scale must both be given with F > 0");
+  for (int f = 0; f < F; ++f)
+    if (!(scale[f] != 0.f) || !std::isfinite(scale[f]) || !std::isfinite(offset[f]))
+      return fail(c, RML_E_INVALID, "rml_load_affine: scale[%d] = %g, offset[%d] = %g", f, scale[f], f, offset[f]);
+  int rc;
+  if ((rc = upload(c, &c->aff_off_dev, offset, F))) return rc;
+  if ((rc = upload(c, &c->aff_scl_dev, scale, F))) return rc;
+  c->aff_F = F;
+  c->aff_enabled = 1;
+  c->aff_shift.resize(F);
+  for (int f = 0; f < F; ++f) c->aff_shift[f] = static_cast<double>(offset[f]) / static_cast<double>(scale[f]);
+  return RML_OK;
+}
+
+int rml_set_precision(rml_ctx* c, int force_f32) {
+  if (!c) return RML_E_INVALID;
+  c->force_f32 = force_f32 ? 1 : 0;
   return RML_OK;
 }
 
@@ -655,13 +829,19 @@ int rml_load_svc_rbf(rml_ctx* c, int C, int F, int n_sv, const int32_t* n_suppor
   const int n_pad = m.n_tile * m.n_chunks;
   std::vector<uint8_t> u8(static_cast<size_t>(n_pad) * m.kpad, 0);
   std::vector<int32_t> norm(n_pad, 0);
-  bool integral = true;
+  // a model behind a per-feature affine lives in standardised space: no integer form
+  const bool per_feature = c->aff_off_dev != nullptr;
+  if (per_feature && c->aff_F != F)
+    return fail(c, RML_E_INVALID, "rml_load_svc_rbf: the loaded per-feature affine has F=%d, the model F=%d", c->aff_F, F);
+  bool integral = !per_feature;
   for (int n = 0; n < n_sv && integral; ++n) {
     int64_t s2 = 0;
     for (int f = 0; f < F; ++f) {
       const double v = sv[static_cast<size_t>(n) * F + f] * feature_scale;
       const double r = std::nearbyint(v);
-      if (std::fabs(v - r) > 1e-4 || r < 0 || r > 255) { integral = false; break; }
+      // float32(u / scale) * scale is within 2e-5 of u for every u in [0,255]; anything further
+      // from an integer is a genuinely non-integral support vector (augmented data)
+      if (std::fabs(v - r) > 2e-5 || r < 0 || r > 255) { integral = false; break; }
       u8[static_cast<size_t>(n) * m.kpad + f] = static_cast<uint8_t>(r);
       s2 += static_cast<int64_t>(r) * static_cast<int64_t>(r);
     }
@@ -669,6 +849,10 @@ int rml_load_svc_rbf(rml_ctx* c, int C, int F, int n_sv, const int32_t* n_suppor
   }
   // 2*max(u.s) and the norm sum must stay inside s32: F * 255^2 * 2 < 2^31  <=>  F <= 16512
   if (static_cast<double>(F) * 65025.0 * 2.0 >= 2147483647.0) integral = false;
+  // many support vectors x many classes can leave no room for a 2-stage operand ring next to the
+  // epilogue tables: such a model takes the digit / general scorer instead of failing at predict
+  m.i8_stages = k2_pick_stages(m.n_tile, n_pad, C * (C - 1) / 2);
+  if (m.i8_stages < 2) integral = false;
   m.integral = integral;
   int rc;
   if (integral) {
@@ -690,13 +874,35 @@ int rml_load_svc_rbf(rml_ctx* c, int C, int F, int n_sv, const int32_t* n_suppor
     if ((rc = upload(c, &m.svnorm, norm.data(), norm.size()))) return rc;
     if ((rc = encode_u8_map(c, &m.map_sv, m.sv_u8, n_sv, F, m.kpad, m.n_tile))) return rc;
   }
-  // digit planes: every component in [0, 256/scale) and room for 3 products per s32 accumulator
+  // digit planes: every (shifted) component in [0, 256/dg_scale) and room for 3 products per s32
+  // accumulator.  Without a per-feature affine dg_scale = feature_scale and the shift is 0; with
+  // one (features standardised as (u - offset_f)/scale_f) the shift offset_f/scale_f makes every
+  // component non-negative — distances are translation invariant — and dg_scale is chosen so that
+  // 255/min|scale_f| still fits 24 bits.
   {
     bool ok = static_cast<double>(F) * 65025.0 * 3.0 < 2147483647.0;
     m.dg_chunks = (n_sv + kDgTileN - 1) / kDgTileN;
     m.dg_pad = m.dg_chunks * kDgTileN;
     const int NP = C * (C - 1) / 2;
     if (k2dg_smem_bytes(m.dg_pad, NP) > 232448) ok = false;
+    m.dg_scale = feature_scale;
+    if (per_feature) {
+      double top = 0.0;
+      // largest standardised-and-shifted value a sensor byte can take: 255 / scale_f
+      std::vector<float> scl(F);
+      cudaMemcpy(scl.data(), c->aff_scl_dev, static_cast<size_t>(F) * 4, cudaMemcpyDeviceToHost);
+      for (int f = 0; f < F; ++f) {
+        if (scl[f] < 0.f) { ok = false; break; }      // a negative scale flips the axis; not a fitted scaler
+        const double v = 255.0 / static_cast<double>(scl[f]);
+        if (v > top) top = v;
+      }
+      for (int n = 0; n < n_sv && ok; ++n)
+        for (int f = 0; f < F; ++f) {
+          const double v = sv[static_cast<size_t>(n) * F + f] + c->aff_shift[f];
+          if (v > top) top = v;
+        }
+      m.dg_scale = top > 0.0 ? 255.5 / top : 1.0;
+    }
     std::vector<uint8_t> dg;
     std::vector<long long> n64(m.dg_pad, 0);
     if (ok) dg.assign(static_cast<size_t>(3) * m.dg_pad * m.kpad, 0);
@@ -704,7 +910,8 @@ int rml_load_svc_rbf(rml_ctx* c, int C, int F, int n_sv, const int32_t* n_suppor
     for (int n = 0; n < n_sv && ok; ++n) {
       unsigned long long s2 = 0;
       for (int f = 0; f < F; ++f) {
-        const double v = std::nearbyint(sv[static_cast<size_t>(n) * F + f] * feature_scale * 65536.0);
+        const double x = sv[static_cast<size_t>(n) * F + f] + (per_feature ? c->aff_shift[f] : 0.0);
+        const double v = std::nearbyint(x * m.dg_scale * 65536.0);
         if (!(v >= 0.0 && v < 16777216.0)) { ok = false; break; }
         const uint32_t X = static_cast<uint32_t>(v);
         const size_t o = static_cast<size_t>(n) * m.kpad + f;
@@ -730,6 +937,7 @@ int rml_load_svc_rbf(rml_ctx* c, int C, int F, int n_sv, const int32_t* n_suppor
       if ((rc = upload(c, &m.sv_digits, dg.data(), dg.size()))) return rc;
       if ((rc = upload(c, &m.svnorm64, n64.data(), n64.size()))) return rc;
       if ((rc = upload(c, &m.pairw_dg, pw.data(), pw.size()))) return rc;
+      if (per_feature && (rc = upload(c, &m.dg_shift, c->aff_shift.data(), static_cast<size_t>(F)))) return rc;
       for (int d = 0; d < 3; ++d)
         if ((rc = encode_u8_map(c, &m.map_sv_dg[d], m.sv_digits + d * plane, n_sv, F, m.kpad, kDgTileN))) return rc;
     }
@@ -800,6 +1008,9 @@ int rml_process_samples(rml_ctx* c, const float* xz, const float* yz, const floa
   p.feats = feats; p.B = B; p.F = feature_len(c, mask); p.scale = scale;
   // scale != 0 applies the context affine: default (0, 255) = common.py:148; (127.5, 127.5) = dnn.py:203
   p.offset = c->aff_offset; p.scale_value = c->aff_scale;
+  p.aff_off = c->aff_off_dev; p.aff_scl = c->aff_scl_dev;
+  if (scale && c->aff_off_dev && c->aff_F != p.F)
+    return fail(c, RML_E_INVALID, "rml_process_samples: the per-feature affine has F=%d, mask %u gives F=%d", c->aff_F, mask, p.F);
   const int64_t total = B * p.F;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 16ll * c->num_sms) blocks = 16ll * c->num_sms;
@@ -852,10 +1063,7 @@ int rml_score(rml_ctx* c, const void* feats, int dtype, const int32_t* norms, in
 
 size_t rml_predict_workspace_bytes(const rml_ctx* c, int64_t B) {
   if (!c || B <= 0) return 256;
-  const int dtype = use_u8_path(c) ? RML_U8 : RML_F32;
-  const size_t stride = feature_stride(c, RML_MASK_ALL, dtype);
-  return align256(static_cast<size_t>(B) * stride * (dtype == RML_U8 ? 1 : 4)) +
-         align256(static_cast<size_t>(B) * 4) + 256;
+  return predict_plan(c, B, RML_MASK_ALL).total;
 }
 
 int rml_predict(rml_ctx* c, const float* cubes, int64_t B, int mode, const int32_t* ijk,
@@ -879,6 +1087,64 @@ int rml_predict_u8(rml_ctx* c, const uint8_t* cubes, int64_t B, int mode, const 
 }  // extern "C"
 
 namespace {
+int reserve_host_pipe(rml_ctx* c, int cube_u8) {
+  HostPipe& hp = c->pipe;
+  // 512 float32 cubes = 246 MB per H2D transfer; uint8 cubes are a quarter of that, so twice the
+  // scans per chunk keeps the transfers long and the launches few
+  const int64_t chunk = cube_u8 ? 1024 : 512;
+  const size_t cube_bytes = static_cast<size_t>(c->sx) * c->sy * c->sz * (cube_u8 ? 1 : 4);
+  // the feature staging depends on the loaded model (u8 rows vs float32 rows + digit planes)
+  const size_t work_need = rml_predict_workspace_bytes(c, chunk);
+  if (hp.chunk == chunk && hp.cube_bytes == cube_bytes && hp.work_bytes >= work_need) return RML_OK;
+  cudaDeviceSynchronize();
+  free_pipe(hp);
+  hp.work_bytes = work_need;
+  for (int i = 0; i < kHostBufs; ++i) {
+    RML_CUDA(c, cudaMalloc(&hp.cubes[i], chunk * cube_bytes));
+    RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.ijk[i]), chunk * 3 * 4));
+    RML_CUDA(c, cudaMalloc(&hp.work[i], hp.work_bytes));
+    RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.proba[i]), chunk * kMaxClasses * 4));
+    RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.label[i]), chunk * 4));
+    RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.known[i]), chunk));
+    RML_CUDA(c, cudaStreamCreateWithFlags(&hp.stream[i], cudaStreamNonBlocking));
+  }
+  hp.chunk = chunk;
+  hp.cube_bytes = cube_bytes;
+  return RML_OK;
+}
+
+// workspace of the small calls: [u8 rows][int32 norms][digit planes + norms], all three present so
+// that the scorer can fall through u8 -> digits -> float64 without another allocation
+size_t small_u8_bytes(const rml_ctx* c, int64_t rows) {
+  const int F = c->model.kind ? c->model.F : feature_len(c, RML_MASK_ALL);
+  return align256(static_cast<size_t>(rows) * round_up(F, 128)) + align256(static_cast<size_t>(rows) * 4);
+}
+size_t small_work_bytes(const rml_ctx* c, int64_t rows) {
+  return small_u8_bytes(c, rows) + digit_scratch_bytes(c, rows) + 256;
+}
+
+int reserve_small(rml_ctx* c, int64_t rows) {
+  SmallPipe& sp = c->small;
+  const int F = c->model.kind ? c->model.F : feature_len(c, RML_MASK_ALL);
+  if (rows > kSmallMax) rows = kSmallMax;
+  if (rows < 1) rows = 1;
+  const size_t work_need = small_work_bytes(c, rows);
+  if (sp.cap >= rows && sp.F == F && sp.work_bytes >= work_need) return RML_OK;
+  cudaDeviceSynchronize();
+  free_small(sp);
+  RML_CUDA(c, cudaMalloc(&sp.cube, static_cast<size_t>(c->sx) * c->sy * c->sz * 4));
+  RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&sp.ijk), rows * 12));
+  RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&sp.feats), static_cast<size_t>(rows) * F * 4));
+  RML_CUDA(c, cudaMalloc(&sp.work, work_need));
+  RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&sp.proba), rows * kMaxClasses * 4));
+  RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&sp.label), rows * 4));
+  RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&sp.known), rows));
+  sp.pinned_bytes = static_cast<size_t>(rows) * (kMaxClasses * 4 + 4 + 1) + 64;
+  RML_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&sp.pinned), sp.pinned_bytes, cudaHostAllocDefault));
+  sp.cap = rows; sp.F = F; sp.work_bytes = work_need;
+  return RML_OK;
+}
+
 // Host buffers in, host buffers out: the batch goes through the GPU in chunks on kHostBufs
 // streams so that the H2D copy of chunk n+1 overlaps the kernels and the D2H copy of chunk n.
 int predict_host_impl(rml_ctx* c, const void* cubes_host, int cube_u8, int64_t B, int mode,
@@ -892,32 +1158,12 @@ int predict_host_impl(rml_ctx* c, const void* cubes_host, int cube_u8, int64_t B
   if (B == 0) return RML_OK;
   DeviceGuard g(c->device);
   HostPipe& hp = c->pipe;
-  // 512 float32 cubes = 246 MB per H2D transfer; uint8 cubes are a quarter of that, so twice the
-  // scans per chunk keeps the transfers long and the launches few
   const int64_t chunk = cube_u8 ? 1024 : 512;
   const size_t cube_bytes = static_cast<size_t>(c->sx) * c->sy * c->sz * (cube_u8 ? 1 : 4);
   const int C = c->model.C;
-  // the feature staging depends on the loaded model (u8 rows vs float32 rows): a model change
-  // after the first call must not leave a workspace that is too small
-  const size_t work_need = rml_predict_workspace_bytes(c, chunk);
-  if (hp.chunk != chunk || hp.cube_bytes != cube_bytes || hp.work_bytes < work_need) {
-    free_pipe(hp);
-    hp.work_bytes = work_need;
-    for (int i = 0; i < kHostBufs; ++i) {
-      RML_CUDA(c, cudaMalloc(&hp.cubes[i], chunk * cube_bytes));
-      RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.ijk[i]), chunk * 3 * 4));
-      RML_CUDA(c, cudaMalloc(&hp.work[i], hp.work_bytes));
-      RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.proba[i]), chunk * kMaxClasses * 4));
-      RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.label[i]), chunk * 4));
-      RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.known[i]), chunk));
-      RML_CUDA(c, cudaStreamCreateWithFlags(&hp.stream[i], cudaStreamNonBlocking));
-    }
-    hp.chunk = chunk;
-    hp.cube_bytes = cube_bytes;
-  }
-  // the general-precision scorer keeps one grow-only scratch per context (dg_planes): chunks of
-  // such a model must not overlap on different streams, so they all take slot 0
-  const int n_slots = use_u8_path(c) ? kHostBufs : 1;
+  if (hp.chunk != chunk || hp.cube_bytes != cube_bytes || hp.work_bytes < rml_predict_workspace_bytes(c, chunk))
+    return fail(c, RML_E_INVALID, "rml_predict_host: staging buffers not reserved for this model / cube type; call "
+                "rml_reserve(ctx, 0, %s) after loading the model", cube_u8 ? "RML_RESERVE_HOST_U8" : "RML_RESERVE_HOST");
   const char* src = static_cast<const char*>(cubes_host);
   int64_t done = 0;
   int slot = 0;
@@ -936,14 +1182,99 @@ int predict_host_impl(rml_ctx* c, const void* cubes_host, int cube_u8, int64_t B
     if (known_host)
       RML_CUDA(c, cudaMemcpyAsync(known_host + done, hp.known[slot], n, cudaMemcpyDeviceToHost, st));
     done += n;
-    slot = (slot + 1) % n_slots;
+    slot = (slot + 1) % kHostBufs;
   }
   for (int i = 0; i < kHostBufs; ++i) RML_CUDA(c, cudaStreamSynchronize(hp.stream[i]));
   return RML_OK;
 }
+
+// status word -> error code (shared by rml_check_status and the host-buffer calls)
+int status_to_rc(rml_ctx* c, const unsigned int h[4]) {
+  if (h[3]) return fail(c, RML_E_INVALID, "derive_targets: %u axis rankings had no finite maximum (NaN / -inf sums); the lowest unused index was emitted", h[3]);
+  if (h[1]) return fail(c, RML_E_INVALID, "SLICE mode: %u scans had a target index outside the cube (numpy IndexError)", h[1]);
+  if (h[2]) return fail(c, RML_E_RANGE, "digit path: %u scans had features outside [0, 256/scale); score them as RML_F32_EXACT", h[2]);
+  if (h[0]) return fail(c, RML_E_NONINTEGRAL, "u8 path: %u warps saw values that are not integers in [0,255] (NaN included); use RML_F32", h[0]);
+  return RML_OK;
+}
+
+// B <= kSmallMax rows already on the device in sp.feats (float32, scaled): score them with the
+// best exact path and bring results + status back with ONE synchronisation in the common case.
+// Order tried: u8 tensor-core scorer (integral model and integral rows) -> multi-digit
+// tensor-core scorer -> float64 CUDA-core scorer; the switch is made on the device status word,
+// never silently on the host.
+int score_small(rml_ctx* c, int64_t B, double min_proba, float* proba_host, int32_t* label_host,
+                uint8_t* known_host, cudaStream_t st) {
+  SmallPipe& sp = c->small;
+  Model& m = c->model;
+  const int C = m.C;
+  unsigned char* pin = sp.pinned;
+  float* pin_proba = reinterpret_cast<float*>(pin);
+  int32_t* pin_label = reinterpret_cast<int32_t*>(pin + static_cast<size_t>(sp.cap) * kMaxClasses * 4);
+  uint8_t* pin_known = reinterpret_cast<uint8_t*>(pin_label + sp.cap);
+  unsigned int* pin_status = reinterpret_cast<unsigned int*>(pin + sp.pinned_bytes - 16);
+  const bool can_u8 = m.kind == 1 && m.integral && !c->force_f32 && !c->aff_off_dev;
+  char* ws = static_cast<char*>(sp.work);
+  for (int attempt = can_u8 ? 0 : 1; attempt < 3; ++attempt) {
+    int rc;
+    if (attempt == 0) {
+      uint8_t* q = reinterpret_cast<uint8_t*>(ws);
+      int32_t* norms = reinterpret_cast<int32_t*>(ws + align256(static_cast<size_t>(sp.cap) * m.kpad));
+      QuantParams qp;
+      qp.feats = sp.feats; qp.out = q; qp.norms = norms; qp.status = c->status; qp.B = B; qp.F = m.F;
+      qp.stride = m.kpad; qp.scale = static_cast<float>(m.feature_scale);
+      k1_quantize<<<static_cast<unsigned>((B + 7) / 8), 256, 0, st>>>(qp);
+      RML_CUDA(c, cudaGetLastError());
+      ++c->launches;
+      rc = score_impl(c, q, RML_U8, norms, B, min_proba, sp.proba, nullptr, sp.label, sp.known, st);
+    } else if (attempt == 1) {
+      if (m.kind == 1 && !m.digits_ok) continue;
+      rc = score_impl(c, sp.feats, RML_F32, nullptr, B, min_proba, sp.proba, nullptr, sp.label, sp.known, st, 0,
+                      nullptr, m.kind == 1 ? ws + small_u8_bytes(c, sp.cap) : nullptr);
+    } else {
+      rc = score_impl(c, sp.feats, RML_F32_EXACT, nullptr, B, min_proba, sp.proba, nullptr, sp.label, sp.known, st);
+    }
+    if (rc) return rc;
+    RML_CUDA(c, cudaMemcpyAsync(pin_proba, sp.proba, B * C * 4, cudaMemcpyDeviceToHost, st));
+    RML_CUDA(c, cudaMemcpyAsync(pin_label, sp.label, B * 4, cudaMemcpyDeviceToHost, st));
+    RML_CUDA(c, cudaMemcpyAsync(pin_known, sp.known, B, cudaMemcpyDeviceToHost, st));
+    RML_CUDA(c, cudaMemcpyAsync(pin_status, c->status, 16, cudaMemcpyDeviceToHost, st));
+    RML_CUDA(c, cudaMemsetAsync(c->status, 0, 16, st));
+    RML_CUDA(c, cudaStreamSynchronize(st));
+    const bool retry = (attempt == 0 && pin_status[0]) || (attempt == 1 && pin_status[2]);
+    if (retry && !pin_status[1] && !pin_status[3]) continue;
+    int src = status_to_rc(c, pin_status);
+    if (src) return src;
+    memcpy(proba_host, pin_proba, B * C * 4);
+    memcpy(label_host, pin_label, B * 4);
+    if (known_host) memcpy(known_host, pin_known, B);
+    return RML_OK;
+  }
+  return fail(c, RML_E_UNSUPPORTED, "score_small: no scorer accepted the features");
+}
 }  // namespace
 
 extern "C" {
+
+int rml_reserve(rml_ctx* c, int64_t max_batch, int flags) {
+  if (!c) return RML_E_INVALID;
+  DeviceGuard g(c->device);
+  if (flags & RML_RESERVE_SCORE) {
+    const Model& m = c->model;
+    if (m.kind == 1 && m.digits_ok && c->dg_cap < max_batch) {
+      cudaDeviceSynchronize();
+      cudaFree(c->dg_planes); cudaFree(c->dg_norms);
+      c->dg_planes = nullptr; c->dg_norms = nullptr; c->dg_cap = 0;
+      RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->dg_planes), align256(static_cast<size_t>(3) * max_batch * m.kpad)));
+      RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->dg_norms), static_cast<size_t>(max_batch) * 8));
+      c->dg_cap = max_batch;
+    }
+  }
+  int rc;
+  if ((flags & RML_RESERVE_HOST) && (rc = reserve_host_pipe(c, 0))) return rc;
+  if ((flags & RML_RESERVE_HOST_U8) && (rc = reserve_host_pipe(c, 1))) return rc;
+  if ((flags & RML_RESERVE_SMALL) && (rc = reserve_small(c, max_batch))) return rc;
+  return RML_OK;
+}
 
 int rml_predict_host(rml_ctx* c, const float* cubes_host, int64_t B, int mode,
                      const int32_t* ijk_host, uint32_t mask, double min_proba, float* proba_host,
@@ -959,6 +1290,130 @@ int rml_predict_host_u8(rml_ctx* c, const uint8_t* cubes_host, int64_t B, int mo
                            label_host, known_host);
 }
 
+// predict.py:56-70 for host features: model.predict_proba(X) + argmax + threshold
+int rml_score_host(rml_ctx* c, const float* feats_host, int64_t B, double min_proba, float* proba_host,
+                   int32_t* label_host, uint8_t* known_host) {
+  if (!c) return RML_E_INVALID;
+  if (c->model.kind == 0) return fail(c, RML_E_NOMODEL, "rml_score_host: no model loaded");
+  if (!feats_host || !proba_host || !label_host || B < 0) return fail(c, RML_E_INVALID, "rml_score_host: null buffer or B<0");
+  if (B == 0) return RML_OK;
+  DeviceGuard g(c->device);
+  SmallPipe& sp = c->small;
+  if (sp.cap < 1 || sp.F != c->model.F || sp.work_bytes < small_work_bytes(c, sp.cap))
+    return fail(c, RML_E_INVALID, "rml_score_host: call rml_reserve(ctx, rows, RML_RESERVE_SMALL) after loading the model");
+  cudaStream_t st = c->aux_stream;
+  const int F = c->model.F, C = c->model.C;
+  for (int64_t done = 0; done < B; done += sp.cap) {
+    const int64_t n = (B - done) < sp.cap ? (B - done) : sp.cap;
+    RML_CUDA(c, cudaMemcpyAsync(sp.feats, feats_host + done * F, static_cast<size_t>(n) * F * 4, cudaMemcpyHostToDevice, st));
+    int rc = score_small(c, n, min_proba, proba_host + done * C, label_host + done,
+                         known_host ? known_host + done : nullptr, st);
+    if (rc) return rc;
+  }
+  return RML_OK;
+}
+
+// One predict.py:93-119 iteration: ONE raw cube (predict.py:90-91) and its T detected targets.
+// The cube crosses PCIe once; every target takes its three slices from it (predict.py:102-107),
+// concat + /255 (common.py:141-149) and the classifier chain, all behind one synchronisation.
+int rml_predict_targets_host(rml_ctx* c, const float* cube_host, int T, const int32_t* ijk_host,
+                             uint32_t mask, double min_proba, float* proba_host, int32_t* label_host,
+                             uint8_t* known_host) {
+  if (!c) return RML_E_INVALID;
+  if (c->model.kind == 0) return fail(c, RML_E_NOMODEL, "rml_predict_targets_host: no model loaded");
+  if (!cube_host || !ijk_host || !proba_host || !label_host || T < 0)
+    return fail(c, RML_E_INVALID, "rml_predict_targets_host: null buffer or T<0");
+  if (T == 0) return RML_OK;
+  if (feature_len(c, mask) != c->model.F)
+    return fail(c, RML_E_INVALID, "rml_predict_targets_host: mask gives F=%d but the model has F=%d", feature_len(c, mask), c->model.F);
+  DeviceGuard g(c->device);
+  SmallPipe& sp = c->small;
+  if (sp.cap < T || sp.F != c->model.F || sp.work_bytes < small_work_bytes(c, sp.cap))
+    return fail(c, RML_E_INVALID, "rml_predict_targets_host: call rml_reserve(ctx, max_targets, RML_RESERVE_SMALL) after loading the model");
+  cudaStream_t st = c->aux_stream;
+  RML_CUDA(c, cudaMemcpyAsync(sp.cube, cube_host, static_cast<size_t>(c->sx) * c->sy * c->sz * 4, cudaMemcpyHostToDevice, st));
+  RML_CUDA(c, cudaMemcpyAsync(sp.ijk, ijk_host, static_cast<size_t>(T) * 12, cudaMemcpyHostToDevice, st));
+  // float32 feature rows exactly as common.process_samples(scale=True) returns them, then the
+  // scorer chain picks the fastest exact path on the device status
+  const Affine aff = c->aff_off_dev ? Affine{0.f, 1.f, 1, c->aff_off_dev, c->aff_scl_dev}
+                                    : Affine{0.f, static_cast<float>(c->model.feature_scale), 1};
+  int rc = project_impl(c, sp.cube, T, RML_MODE_SLICE, sp.ijk, mask, RML_F32, sp.feats, nullptr, st, 0, nullptr,
+                        &aff, 0, /*cube_stride=*/0);
+  if (rc) return rc;
+  return score_small(c, T, min_proba, proba_host, label_host, known_host, st);
+}
+
+// ------------------------------------------------------------------------------ label exchange
+static int nccl_load(rml_ctx* c) {
+  if (g_nccl.handle) return RML_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // already in the process (torch)?
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h)
+    if (const char* e = getenv("RML_NCCL_LIB")) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(c, RML_E_UNSUPPORTED, "NCCL not found (libnccl.so.2 / RML_NCCL_LIB): %s", dlerror());
+  g_nccl.GetUniqueId = reinterpret_cast<int (*)(rml_nccl_uid*)>(dlsym(h, "ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<int (*)(void**, int, rml_nccl_uid, int)>(dlsym(h, "ncclCommInitRank"));
+  g_nccl.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(h, "ncclAllGather"));
+  g_nccl.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+  g_nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy)
+    return fail(c, RML_E_UNSUPPORTED, "NCCL symbols missing in the loaded library");
+  g_nccl.handle = h;
+  return RML_OK;
+}
+
+int rml_comm_unique_id(rml_ctx* c, void* id128) {
+  if (!c || !id128) return RML_E_INVALID;
+  int rc = nccl_load(c);
+  if (rc) return rc;
+  rml_nccl_uid id;
+  const int r = g_nccl.GetUniqueId(&id);
+  if (r) return fail(c, RML_E_CUDA, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  memcpy(id128, &id, 128);
+  return RML_OK;
+}
+
+int rml_comm_init(rml_ctx* c, int rank, int world, const void* id128) {
+  if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(c, RML_E_INVALID, "rml_comm_init: bad arguments");
+  int rc = nccl_load(c);
+  if (rc) return rc;
+  DeviceGuard g(c->device);
+  if (c->nccl_comm) { g_nccl.CommDestroy(c->nccl_comm); c->nccl_comm = nullptr; }
+  rml_nccl_uid id;
+  memcpy(&id, id128, 128);
+  const int r = g_nccl.CommInitRank(&c->nccl_comm, world, id, rank);
+  if (r) return fail(c, RML_E_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  c->nccl_rank = rank; c->nccl_world = world;
+  return RML_OK;
+}
+
+int rml_comm_destroy(rml_ctx* c) {
+  if (!c) return RML_E_INVALID;
+  if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+  c->nccl_comm = nullptr; c->nccl_world = 1; c->nccl_rank = 0;
+  return RML_OK;
+}
+
+// ONE all-gather of the int32 labels per batch.  send_dev may be the rank's own
+// slice of recv_dev (recv_dev + rank * count): rml_predict then writes the labels straight into
+// the gather buffer and NCCL runs in place, no copy between the scorer and the collective.
+int rml_allgather_labels(rml_ctx* c, const int32_t* send_dev, int32_t* recv_dev, int64_t count, rml_stream stream) {
+  if (!c) return RML_E_INVALID;
+  if (!send_dev || !recv_dev || count < 0) return fail(c, RML_E_INVALID, "rml_allgather_labels: null buffer or count<0");
+  DeviceGuard g(c->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->nccl_world == 1 && !c->nccl_comm) {
+    if (send_dev != recv_dev)
+      RML_CUDA(c, cudaMemcpyAsync(recv_dev, send_dev, static_cast<size_t>(count) * 4, cudaMemcpyDeviceToDevice, st));
+    return RML_OK;
+  }
+  if (!c->nccl_comm) return fail(c, RML_E_INVALID, "rml_allgather_labels: call rml_comm_init first");
+  const int r = g_nccl.AllGather(send_dev, recv_dev, static_cast<size_t>(count), /*ncclInt32*/ 2, c->nccl_comm, st);
+  if (r) return fail(c, RML_E_CUDA, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return RML_OK;
+}
+
 int rml_check_status(rml_ctx* c, rml_stream stream) {
   if (!c) return RML_E_INVALID;
   DeviceGuard g(c->device);
@@ -967,10 +1422,7 @@ int rml_check_status(rml_ctx* c, rml_stream stream) {
   RML_CUDA(c, cudaMemcpyAsync(h, c->status, 16, cudaMemcpyDeviceToHost, st));
   RML_CUDA(c, cudaMemsetAsync(c->status, 0, 16, st));
   RML_CUDA(c, cudaStreamSynchronize(st));
-  if (h[1]) return fail(c, RML_E_INVALID, "SLICE mode: %u scans had a target index outside the cube (numpy IndexError)", h[1]);
-  if (h[2]) return fail(c, RML_E_RANGE, "digit path: %u scans had features outside [0, 256/scale); score them as RML_F32_EXACT", h[2]);
-  if (h[0]) return fail(c, RML_E_NONINTEGRAL, "u8 path: %u warps saw values that are not integers in [0,255]; use RML_F32", h[0]);
-  return RML_OK;
+  return status_to_rc(c, h);
 }
 
 int64_t rml_launch_count(const rml_ctx* c) { return c ? c->launches : 0; }
@@ -1026,10 +1478,9 @@ int rml_derive_targets(rml_ctx* c, const float* cubes, int64_t B, int num_target
   if (B == 0) return RML_OK;
   DeviceGuard g(c->device);
   DeriveParams p;
-  p.cubes = cubes; p.ijk = ijk; p.sums = sums; p.B = B; p.sx = c->sx; p.sy = c->sy; p.sz = c->sz;
+  p.cubes = cubes; p.ijk = ijk; p.sums = sums; p.status = c->status; p.B = B; p.sx = c->sx; p.sy = c->sy; p.sz = c->sz;
   p.T = num_targets;
   const int smem = (c->sx + c->sy + c->sz + 8 * c->sz + c->sx * c->sy) * 4;
-  RML_CUDA(c, cudaFuncSetAttribute(k0_derive_targets, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = static_cast<int>(B < 8ll * c->num_sms ? B : 8ll * c->num_sms);
   k0_derive_targets<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
   RML_CUDA(c, cudaGetLastError());
@@ -1093,7 +1544,9 @@ int rml_process_samples_zoom(rml_ctx* c, const float* xz, int64_t stride_xz, con
   }
   p.feats = feats; p.B = B; p.F = off; p.scale = scale;
   p.offset = c->aff_offset; p.scale_value = c->aff_scale;
-  RML_CUDA(c, cudaFuncSetAttribute(k0_zoom_concat, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  p.aff_off = c->aff_off_dev; p.aff_scl = c->aff_scl_dev;
+  if (scale && c->aff_off_dev && c->aff_F != p.F)
+    return fail(c, RML_E_INVALID, "rml_process_samples_zoom: the per-feature affine has F=%d, the zoomed row F=%d", c->aff_F, p.F);
   const int gx = static_cast<int>(B < 4ll * c->num_sms ? B : 4ll * c->num_sms);
   k0_zoom_concat<<<dim3(gx, 3), 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
   RML_CUDA(c, cudaGetLastError());
@@ -1254,8 +1707,8 @@ int rml_net_finish(rml_ctx* c) {
 // Workspace plan of the network forward:
 //   [ tower chunk: images | ping | pong ] [ flat bf16 tower output of a dense group ] [ f32 features of a chunk ]
 // The conv towers run chunk by chunk (their activations are large); the tcgen05 dense stack runs
-// once per dense group of up to kDenseGroup scans so that it has >= 128 tiles to spread over the SMs.
-constexpr int64_t kDenseGroup = 16384;
+// once per dense group of up to kDenseGroup scans so that it has one tile for every SM.
+constexpr int64_t kDenseGroup = 148 * 128;   // one 128-scan tile per SM: the dense stack fills the chip
 static size_t net_tower_bytes_per_scan(const rml_ctx* c) {
   const Net& n = c->net;
   size_t img = static_cast<size_t>(3) * n.R * n.R * 4;
@@ -1320,7 +1773,6 @@ static int net_resize(rml_ctx* c, const float* feats, int64_t n_scans, float* im
     const int sm = (ph[b] * pw[b] + ph[b] * n.R) * 4;
     if (sm > smem_max) smem_max = sm;
   }
-  RML_CUDA(c, cudaFuncSetAttribute(k3_resize_pil, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   const int gx = static_cast<int>(n_scans < 4ll * c->num_sms ? n_scans : 4ll * c->num_sms);
   k3_resize_pil<<<dim3(gx, 3), 256, smem_max, st>>>(rp);
   RML_CUDA(c, cudaGetLastError());
@@ -1378,13 +1830,8 @@ static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_
     fp.act = cv.act; fp.alpha = n.alpha;
     fp.out = reinterpret_cast<__nv_bfloat16*>(ping);
     const int gx = static_cast<int>(n_scans < 8ll * c->num_sms ? n_scans : 8ll * c->num_sms);
-    if (cv.cout == 64) {
-      RML_CUDA(c, cudaFuncSetAttribute(k34_resize_conv1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-      k34_resize_conv1<2><<<dim3(gx, 3), 256, smem_max, st>>>(fp);
-    } else {
-      RML_CUDA(c, cudaFuncSetAttribute(k34_resize_conv1<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-      k34_resize_conv1<4><<<dim3(gx, 3), 256, smem_max, st>>>(fp);
-    }
+    if (cv.cout == 64) k34_resize_conv1<2><<<dim3(gx, 3), 256, smem_max, st>>>(fp);
+    else k34_resize_conv1<4><<<dim3(gx, 3), 256, smem_max, st>>>(fp);
     RML_CUDA(c, cudaGetLastError());
     ++c->launches;
     cur = ping;
@@ -1420,7 +1867,6 @@ static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_
       gp.out = reinterpret_cast<__nv_bfloat16*>(dst);
       gp.stages = cg_pick_stages(cv.cout);
       const int smem = cg_smem_bytes(cv.cout, gp.stages);
-      RML_CUDA(c, cudaFuncSetAttribute(k4_conv_igemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       const int64_t tiles = gp.n_img * gp.tiles_per_img;
       const int grid = static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
       k4_conv_igemm<<<grid, kCgThreads, smem, st>>>(map_x, cv.map_w, gp);
@@ -1446,7 +1892,6 @@ static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_
       cp.act = cv.act; cp.alpha = n.alpha;
       cp.out_bf16 = (last || n.use_igemm) ? 1 : 0;           // bf16 feeds the tensor-core layers
       const int smem = 9 * cv.cin * kConvCoutTile * 4;
-      RML_CUDA(c, cudaFuncSetAttribute(k4_conv3x3s2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       const int64_t pixels = n_scans * ho * ho;
       int64_t gx = (pixels + 255) / 256;
       if (gx > 8ll * c->num_sms) gx = 8ll * c->num_sms;
@@ -1470,12 +1915,11 @@ static int net_dense(rml_ctx* c, const uint16_t* flat, int64_t n_scans, float* p
   K5Params kp;
   kp.B = n_scans; kp.k_blocks = n.K / kK5BlockK; kp.C = n.C; kp.head = n.head;
   kp.kpg = (kp.k_blocks % 4 == 0) ? 4 : (kp.k_blocks % 2 == 0) ? 2 : 1;
-  if (const char* e = getenv("RML_K5_KPG")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && kp.k_blocks % v == 0) kp.kpg = v; }
+  if (c->k5_kpg && kp.k_blocks % c->k5_kpg == 0) kp.kpg = c->k5_kpg;
   kp.act1 = n.act1; kp.act2 = n.act2; kp.alpha = n.alpha;
   kp.b1 = n.b1; kp.w2 = n.w2; kp.b2 = n.b2; kp.w3 = n.w3; kp.b3 = n.b3;
   kp.proba = proba; kp.logits = logits; kp.label = label;
   const int smem5 = k5_smem_bytes();
-  RML_CUDA(c, cudaFuncSetAttribute(k5_dense_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5));
   const int64_t tiles = (n_scans + kK5BlockM - 1) / kK5BlockM;
   const int grid = static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
   k5_dense_stack<<<grid, kK5Threads, smem5, st>>>(map_act, n.map_w1, kp);

@@ -84,5 +84,8 @@ class ShardedClassifier:
 
     def predict_shard(self, local_cubes, total: int | None = None, **kw):
         proba, label, known = self.engine.predict(local_cubes, **kw)
+        # non-integral voxels / bad slice indices must surface on the rank that saw them BEFORE
+        # its labels are published to every other rank
+        self.engine.check_status()
         labels_all = allgather_labels(label, total)
         return proba, label, known, labels_all

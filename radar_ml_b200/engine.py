@@ -12,8 +12,9 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (F32, F32_EXACT, MASK_ALL, MODE_MAX, MODE_SLICE, U8, NonIntegralInput,
-                   OutOfRangeInput, RadarMLError, check)
+from ._lib import (F32, F32_EXACT, MASK_ALL, MODE_MAX, MODE_SLICE, RESERVE_HOST, RESERVE_HOST_U8,
+                   RESERVE_SCORE, RESERVE_SMALL, U8, NonIntegralInput, OutOfRangeInput,
+                   RadarMLError, check)
 
 SX, SY, SZ = 22, 31, 176  # common.py:25-27 -> predict.py:74-76
 
@@ -48,6 +49,8 @@ class Engine:
         self.params = None
         self.dims = (SX, SY, SZ)
         self._work = None
+        self._reserved = {}       # flag -> rows reserved for the currently loaded model
+        self.affine_tables = None
 
     def close(self):
         if getattr(self, "ctx", None) is not None and self.ctx:
@@ -74,6 +77,33 @@ class Engine:
 
     def set_affine(self, offset=0.0, scale=255.0, enabled=True):
         check(self.ctx, self.lib.rml_set_affine(self.ctx, offset, scale, 1 if enabled else 0))
+
+    def load_affine(self, offset=None, scale=None):
+        """Per-feature (x - offset[f]) / scale[f] (a fitted StandardScaler's mean_ / scale_);
+        None, None restores the reference's /255 (common.py:148).  Load it BEFORE the model."""
+        if offset is None and scale is None:
+            check(self.ctx, self.lib.rml_load_affine(self.ctx, None, None, 0))
+            self.affine_tables = None
+        else:
+            off = np.ascontiguousarray(offset, dtype=np.float32)
+            scl = np.ascontiguousarray(scale, dtype=np.float32)
+            if off.shape != scl.shape or off.ndim != 1:
+                raise ValueError("offset and scale must be 1-D arrays of the same length")
+            check(self.ctx, self.lib.rml_load_affine(self.ctx, _np_ptr(off), _np_ptr(scl), off.shape[0]))
+            self.affine_tables = (off, scl)
+        self._reserved = {}
+
+    def set_precision(self, force_f32: bool):
+        """True: rml_predict* emit float32 features (real-valued cubes); False: automatic."""
+        check(self.ctx, self.lib.rml_set_precision(self.ctx, 1 if force_f32 else 0))
+        self._reserved = {}
+        self._work = None
+
+    def reserve(self, rows: int, flag: int):
+        """Library-owned staging is created here, never inside a hot entry point."""
+        if self._reserved.get(flag, -1) < rows:
+            check(self.ctx, self.lib.rml_reserve(self.ctx, int(rows), flag))
+            self._reserved[flag] = rows
 
     def feature_len(self, mask=MASK_ALL):
         return self.lib.rml_feature_len(self.ctx, mask_bits(mask))
@@ -105,6 +135,8 @@ class Engine:
         else:
             raise ValueError(p.kind)
         self.params = p
+        self._reserved = {}
+        self._work = None
 
     @property
     def model_is_integral(self) -> bool:
@@ -230,6 +262,8 @@ class Engine:
             dec = torch.empty((B,) if Cn == 2 else (B, Cn), device=self.device, dtype=torch.float32)
         if B == 0:
             return (proba, label, known.bool()) + ((dec,) if want_decision else ())
+        if dtype == F32:
+            self.reserve(B, RESERVE_SCORE)
         check(self.ctx, self.lib.rml_score(self.ctx, _ptr(feats), dtype, _ptr(norms), B,
                                            float(min_proba), _ptr(proba), _ptr(dec), _ptr(label),
                                            _ptr(known), self._stream()))
@@ -247,27 +281,44 @@ class Engine:
         return out, norms
 
     def score_features_host(self, X: np.ndarray, min_proba=0.7):
-        """model.predict_proba(X) for host features as common.process_samples(scale=True) makes
-        them.  Integral features of an integral model run on the tensor cores; anything else
-        runs the exact general-precision kernel (decided by an explicit device-side check)."""
-        x = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).to(self.device)
-        use_u8 = self.params.kind == "svc_rbf" and self.model_is_integral
-        if use_u8:
-            q, norms = self.quantize(x)
-            try:
-                self.check_status()
-            except NonIntegralInput:
-                use_u8 = False
-        if use_u8:
-            proba, label, known = self.score(q, norms, min_proba)
-        else:
-            proba, label, known = self.score(x, None, min_proba)
-            try:
-                self.check_status()
-            except OutOfRangeInput:      # negative / oversize values: float64 CUDA-core scorer
-                proba, label, known = self.score(x, None, min_proba, exact=True)
-        torch.cuda.synchronize(self.device)
-        return proba.cpu().numpy(), label.cpu().numpy(), known.cpu().numpy()
+        """model.predict_proba(X) (+ argmax, >= min_proba) for host features as
+        common.process_samples(scale=True) makes them: one C call (rml_score_host).  Integral
+        rows of an integral model run on the integer tensor-core scorer, anything else on the
+        exact multi-digit one or the float64 one — decided on the device, never silently."""
+        if self.params is None:
+            raise RadarMLError(_lib.E_NOMODEL, "no model loaded")
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        B = X.shape[0]
+        Cn = self.params.n_classes
+        proba = np.empty((B, Cn), dtype=np.float32)
+        label = np.empty((B,), dtype=np.int32)
+        known = np.empty((B,), dtype=np.uint8)
+        if B:
+            self.reserve(min(B, 1024), RESERVE_SMALL)
+            check(self.ctx, self.lib.rml_score_host(self.ctx, _np_ptr(X), B, float(min_proba),
+                                                    _np_ptr(proba), _np_ptr(label), _np_ptr(known)))
+        return proba, label, known
+
+    def predict_targets_host(self, cube: np.ndarray, ijk, mask=MASK_ALL, min_proba=0.7):
+        """One predict.py:93-119 iteration: ONE raw cube [sx,sy,sz] float32 and the (i,j,k) of its
+        T targets -> (proba [T,C], label [T], known [T]).  The cube is uploaded once."""
+        if self.params is None:
+            raise RadarMLError(_lib.E_NOMODEL, "no model loaded")
+        cube = np.ascontiguousarray(cube, dtype=np.float32)
+        if cube.shape != tuple(self.dims):
+            raise ValueError("cube must have shape %s" % (tuple(self.dims),))
+        ij = np.ascontiguousarray(ijk, dtype=np.int32).reshape(-1, 3)
+        T = ij.shape[0]
+        Cn = self.params.n_classes
+        proba = np.empty((T, Cn), dtype=np.float32)
+        label = np.empty((T,), dtype=np.int32)
+        known = np.empty((T,), dtype=np.uint8)
+        if T:
+            self.reserve(max(T, 8), RESERVE_SMALL)
+            check(self.ctx, self.lib.rml_predict_targets_host(
+                self.ctx, _np_ptr(cube), T, _np_ptr(ij), mask_bits(mask), float(min_proba),
+                _np_ptr(proba), _np_ptr(label), _np_ptr(known)))
+        return proba, label, known
 
     # ------------------------------------------------------------------ K1 -> K2
     def workspace(self, B):
@@ -328,8 +379,45 @@ class Engine:
             if ijk is None:
                 raise ValueError("slice mode needs ijk [B,3] int32")
             ij = np.ascontiguousarray(ijk, dtype=np.int32)
-        fn = self.lib.rml_predict_host_u8 if cubes.dtype == np.uint8 else self.lib.rml_predict_host
-        check(self.ctx, fn(self.ctx, _np_ptr(cubes), B, md, _np_ptr(ij), mask_bits(mask),
-                           float(min_proba), _np_ptr(proba), _np_ptr(label), _np_ptr(known)))
-        self.check_status()
+        u8 = cubes.dtype == np.uint8
+        fn = self.lib.rml_predict_host_u8 if u8 else self.lib.rml_predict_host
+        args = (self.ctx, _np_ptr(cubes), B, md, _np_ptr(ij), mask_bits(mask), float(min_proba),
+                _np_ptr(proba), _np_ptr(label), _np_ptr(known))
+        self.reserve(0, RESERVE_HOST_U8 if u8 else RESERVE_HOST)
+        check(self.ctx, fn(*args))
+        try:
+            self.check_status()
+        except NonIntegralInput:
+            # real-valued float32 cubes (the reference accepts any float32 cube): same call with
+            # float32 features and the exact general-precision scorer
+            if u8:
+                raise
+            self.set_precision(True)
+            try:
+                self.reserve(0, RESERVE_HOST)
+                check(self.ctx, fn(*args))
+                try:
+                    self.check_status()
+                except OutOfRangeInput:
+                    raise
+            finally:
+                self.set_precision(False)
         return proba, label, known
+
+    # ------------------------------------------------------------------ label exchange (C ABI)
+    def comm_init(self, rank: int, world: int, unique_id: bytes | None = None):
+        """NCCL communicator of this context.  rank 0 calls ``comm_unique_id()`` and hands the
+        128 bytes to the others through any host channel (e.g. torch.distributed broadcast)."""
+        buf = C.create_string_buffer(unique_id, 128)
+        check(self.ctx, self.lib.rml_comm_init(self.ctx, rank, world, buf))
+
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        check(self.ctx, self.lib.rml_comm_unique_id(self.ctx, buf))
+        return buf.raw
+
+    def allgather_labels(self, send, recv):
+        """ONE ncclAllGather of int32 labels on the current stream; ``send`` may be the rank's
+        slice of ``recv`` (in place)."""
+        check(self.ctx, self.lib.rml_allgather_labels(self.ctx, _ptr(send), _ptr(recv), send.numel(),
+                                                      self._stream()))

@@ -101,11 +101,19 @@ class GpuCalibratedClassifier:
     def from_sklearn(cls, cal, engine=None, device: int = 0, feature_scale: float = RADAR_MAX):
         return cls(from_sklearn(cal, feature_scale), engine=engine, device=device)
 
+    def bind(self):
+        """The native context holds ONE model: if another wrapper sharing this engine loaded its
+        own since, load ours again before scoring (two models used alternately in one process
+        must never score with each other's weights)."""
+        if self.engine.params is not self.params:
+            self.engine.load_model(self.params)
+        return self.engine
+
     def predict_proba(self, X):
         X = np.ascontiguousarray(X, dtype=np.float32)
         if X.ndim != 2 or X.shape[1] != self.params.n_features:
             raise ValueError("X has shape %s, expected (n, %d)" % (X.shape, self.params.n_features))
-        proba, _, _ = self.engine.score_features_host(X)
+        proba, _, _ = self.bind().score_features_host(X)
         return proba.astype(np.float64)
 
     def predict(self, X):

@@ -72,8 +72,9 @@ def classify_cubes(cubes, model, le=None, min_proba=0.7, mode='max', ijk=None,
     the class names when ``le`` is given.
     """
     import torch
+    from ._lib import NonIntegralInput
     gm = as_gpu_model(model)
-    eng = gm.engine
+    eng = gm.bind()
     if isinstance(cubes, np.ndarray):
         P, lab, known = eng.predict_host(np.ascontiguousarray(cubes, dtype=np.float32), mode=mode,
                                          ijk=ijk, mask=proj_mask, min_proba=min_proba)
@@ -83,7 +84,19 @@ def classify_cubes(cubes, model, le=None, min_proba=0.7, mode='max', ijk=None,
             ijk = torch.as_tensor(np.asarray(ijk), dtype=torch.int32)
         Pd, labd, knownd = eng.predict(cubes, mode=mode, ijk=ijk, mask=proj_mask,
                                        min_proba=min_proba)
-        eng.check_status()
+        try:
+            eng.check_status()
+        except NonIntegralInput:
+            # real-valued float32 cubes: float32 features + the exact general-precision scorer
+            if cubes.dtype != torch.float32:
+                raise
+            eng.set_precision(True)
+            try:
+                Pd, labd, knownd = eng.predict(cubes, mode=mode, ijk=ijk, mask=proj_mask,
+                                               min_proba=min_proba)
+                eng.check_status()
+            finally:
+                eng.set_precision(False)
         P, lab, known = Pd.cpu().numpy(), labd.cpu().numpy(), knownd.cpu().numpy().astype(bool)
     best = P[np.arange(P.shape[0]), lab]
     if le is None:
@@ -97,7 +110,7 @@ def _classify_zoomed(cubes, ijk, gm, le, min_proba, proj_mask, proj_zoom, dims):
     scan arena's size (K1), ndimage.zoom to the training size as separable operators
     (common.py:143), /255, then the general-precision scorer (zoomed values are not integers)."""
     import torch
-    eng = gm.engine
+    eng = gm.bind()
     size_x, size_y, size_z = dims
     saved = eng.dims
     eng.set_arena(size_x, size_y, size_z)
@@ -168,11 +181,15 @@ def predict(min_proba, model, le, proj_mask, radar=None, max_scans=None):
             ys = np.array([t.yPosCm for t in targets], dtype=np.float64)
             zs = np.array([t.zPosCm for t in targets], dtype=np.float64)
             ijk = np.asarray(common.calculate_matrix_indices(xs, ys, zs, size_x, size_y, size_z))
-            cubes = np.ascontiguousarray(np.broadcast_to(raw_image_np, (n,) + raw_image_np.shape))
             if common._unit_zoom(proj_zoom, proj_mask):
-                lab, best, known, P, names = classify_cubes(cubes, gm, le, min_proba, mode='slice',
-                                                            ijk=ijk.reshape(n, 3), proj_mask=proj_mask)
+                # one cube, n index triples: the cube crosses PCIe once (rml_predict_targets_host)
+                P, lab, known = gm.bind().predict_targets_host(raw_image_np, ijk.reshape(n, 3),
+                                                               mask=proj_mask, min_proba=min_proba)
+                known = known.astype(bool)
+                best = P[np.arange(n), lab]
+                names = np.where(known, np.asarray(le.classes_)[lab], 'Unknown')
             else:
+                cubes = np.ascontiguousarray(np.broadcast_to(raw_image_np, (n,) + raw_image_np.shape))
                 lab, best, known, P, names = _classify_zoomed(
                     cubes, ijk.reshape(n, 3), gm, le, min_proba, proj_mask, proj_zoom,
                     (size_x, size_y, size_z))

@@ -42,6 +42,22 @@ def main():
     lo2, hi2 = shard_range(even, rank, world)
     _, _, _, g2 = sc.predict_shard(cubes[lo2:hi2].contiguous(), even)
     ok = ok and bool(torch.equal(g2.cpu(), full_label.cpu()[:even]))
+    if "--c-abi" in sys.argv:
+        # the same exchange through the C ABI: labels written in place into the gather buffer by
+        # rml_predict, then rml_allgather_labels (ncclAllGather via dlopen) — SURVEY.md §8b/§8e
+        box = [eng.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init(rank, world, box[0])
+        n = even // world
+        buf = torch.full((even,), -1, device="cuda", dtype=torch.int32)
+        mine = buf[rank * n:(rank + 1) * n]
+        out = (torch.empty((n, 3), device="cuda"), mine, torch.empty((n,), device="cuda", dtype=torch.uint8))
+        eng.predict(cubes[lo2:hi2].contiguous(), out=out)
+        eng.check_status()
+        eng.allgather_labels(mine, buf)
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(buf.cpu(), full_label.cpu()[:even]))
+        eng.lib.rml_comm_destroy(eng.ctx)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
