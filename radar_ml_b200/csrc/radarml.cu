@@ -22,6 +22,7 @@
 #include "k2_score.cuh"
 #include "k2_digits.cuh"
 #include "k3_net.cuh"
+#include "k6_tower.cuh"
 #include "k0_extras.cuh"
 
 using namespace rml;
@@ -130,6 +131,12 @@ struct Net {
   int2* bv[3] = {nullptr, nullptr, nullptr};
   int ksh[3] = {0, 0, 0}, ksv[3] = {0, 0, 0};
   CUtensorMap map_w1;
+  // fused tower kernel (k6_tower.cuh): 0 off, 1 = dnn (resize + layer 1 + layer 2 on chip),
+  // 2 = sgan (resize + layer 1 on the tensor cores, NHWC bf16 out)
+  int tower_mode = 0;
+  uint16_t* t6_w1 = nullptr;   // [3][C1][32] bf16: whi(9) | whi(9) | wlo(9) | 0(5)
+  float* t6_b1 = nullptr;      // [3][C1]
+  int t6_ctas[3] = {0, 0, 0};
 };
 
 }  // namespace
@@ -347,6 +354,8 @@ int set_kernel_attributes(rml_ctx* c) {
   RML_CUDA(c, opt_in_smem(k4_conv3x3s2));
   RML_CUDA(c, opt_in_smem(k4_conv_igemm));
   RML_CUDA(c, opt_in_smem(k5_dense_stack));
+  RML_CUDA(c, opt_in_smem(k6_tower<64, true, 1>));
+  RML_CUDA(c, opt_in_smem(k6_tower<128, false, 2>));
   return RML_OK;
 }
 
@@ -631,6 +640,7 @@ void free_net(Net& n) {
     cudaFree(cv.wt_bf16); cudaFree(cv.bias3);
   }
   cudaFree(n.w1t); cudaFree(n.b1); cudaFree(n.w2); cudaFree(n.b2); cudaFree(n.w3); cudaFree(n.b3);
+  cudaFree(n.t6_w1); cudaFree(n.t6_b1);
   for (int b = 0; b < 3; ++b) { cudaFree(n.kh[b]); cudaFree(n.kv[b]); cudaFree(n.bh[b]); cudaFree(n.bv[b]); }
   n = Net();
 }
@@ -1700,6 +1710,62 @@ int rml_net_finish(rml_ctx* c) {
       if ((rc = encode_bf16_map(c, &cv.map_w, cv.wt_bf16, 3 * cv.cout, K, cv.cout))) return rc;
     }
   }
+  // fused tower kernel: dnn.py's towers (80x80 -> Conv 64 -> Conv 32) run entirely on chip; sgan.py's
+  // first layer (128x128 -> Conv 128) moves to the tensor cores
+  n.tower_mode = 0;
+  if (ok && n.fuse_resize) {
+    const NetConv& c0 = n.convs[0];
+    if (n.R == 80 && n.convs.size() == 2 && c0.cout == 64 && n.convs[1].cout == 32 && c0.act == 1 &&
+        n.convs[1].act == 1 && c->sx * c->sz <= 31 * 176 && c->sy * c->sz <= 31 * 176 && c->sx <= 31 && c->sy <= 31)
+      n.tower_mode = 1;
+    else if (n.R == 128 && c0.cout == 128 && c0.act == 2 && n.alpha > 0.f && n.alpha < 1.f && c->sx * c->sz <= 31 * 176 && c->sy * c->sz <= 31 * 176 &&
+             c->sx <= 31 && c->sy <= 31)
+      n.tower_mode = 2;
+    if (const char* e = getenv("RML_NET_TOWER")) { if (atoi(e) == 0) n.tower_mode = 0; }
+  }
+  if (n.tower_mode) {
+    const NetConv& c0 = n.convs[0];
+    const int C1 = c0.cout;
+    auto bf16_rn = [](float v) {
+      uint32_t u;
+      memcpy(&u, &v, 4);
+      u = (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+      return static_cast<uint16_t>(u);
+    };
+    auto bf16_to_f = [](uint16_t h) {
+      const uint32_t u = static_cast<uint32_t>(h) << 16;
+      float v;
+      memcpy(&v, &u, 4);
+      return v;
+    };
+    std::vector<uint16_t> w1(static_cast<size_t>(3) * C1 * kT6K1, 0);
+    std::vector<float> b1(static_cast<size_t>(3) * C1);
+    for (int br = 0; br < 3; ++br)
+      for (int co = 0; co < C1; ++co) {
+        b1[br * C1 + co] = c0.b_host[br][co];
+        uint16_t* row = &w1[(static_cast<size_t>(br) * C1 + co) * kT6K1];
+        for (int tap = 0; tap < 9; ++tap) {
+          const float w = c0.w_host[br][static_cast<size_t>(tap) * C1 + co];     // HWIO with cin = 1
+          const uint16_t hi = bf16_rn(w);
+          const uint16_t lo = bf16_rn(w - bf16_to_f(hi));
+          row[tap] = hi; row[9 + tap] = hi; row[18 + tap] = lo;                  // pairs with A: hi | lo | hi
+        }
+        // the bias rides in the GEMM: A carries 1.0 in columns 27 and 28
+        const uint16_t bhi = bf16_rn(c0.b_host[br][co]);
+        row[27] = bhi;
+        row[28] = bf16_rn(c0.b_host[br][co] - bf16_to_f(bhi));
+      }
+    if ((rc = upload(c, &n.t6_w1, w1.data(), w1.size()))) return rc;
+    if ((rc = upload(c, &n.t6_b1, b1.data(), b1.size()))) return rc;
+    // persistent CTAs per branch, proportional to the per-image cost (resize rows differ: 22 / 31 / 22)
+    int split[3] = {50, 52, 46};
+    if (const char* e = getenv("RML_T6_SPLIT")) sscanf(e, "%d,%d,%d", &split[0], &split[1], &split[2]);
+    const int tot = split[0] + split[1] + split[2];
+    n.t6_ctas[0] = c->num_sms * split[0] / tot;
+    n.t6_ctas[1] = c->num_sms * split[1] / tot;
+    n.t6_ctas[2] = c->num_sms - n.t6_ctas[0] - n.t6_ctas[1];
+    for (int b = 0; b < 3; ++b) if (n.t6_ctas[b] < 1) n.tower_mode = 0;
+  }
   n.ready = true;
   return RML_OK;
 }
@@ -1799,8 +1865,38 @@ static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_
   float* images = reinterpret_cast<float*>(ws);
   float* ping = reinterpret_cast<float*>(ws + img_b);
   float* pong = reinterpret_cast<float*>(ws + img_b + act_b);
-  const bool fuse1 = feats && n.use_igemm && n.fuse_resize && (n.convs[0].cout == 64 || n.convs[0].cout == 128);
-  if (feats && !fuse1) {
+  if (n.tower_mode) {
+    TowerParams tp;
+    tp.images = feats ? nullptr : images_in;
+    tp.rz.feats = feats; tp.rz.images = nullptr; tp.rz.B = n_scans; tp.rz.F = feature_len(c, RML_MASK_ALL); tp.rz.R = n.R;
+    const int ph[3] = {c->sx, c->sy, c->sx}, pw[3] = {c->sz, c->sz, c->sy};
+    const int poff[3] = {0, c->sx * c->sz, c->sx * c->sz + c->sy * c->sz};
+    for (int b = 0; b < 3; ++b) {
+      tp.rz.ph[b] = ph[b]; tp.rz.pw[b] = pw[b]; tp.rz.poff[b] = poff[b];
+      tp.rz.kh[b] = n.kh[b]; tp.rz.kv[b] = n.kv[b]; tp.rz.bh[b] = n.bh[b]; tp.rz.bv[b] = n.bv[b];
+      tp.rz.ksh[b] = n.ksh[b]; tp.rz.ksv[b] = n.ksv[b];
+      tp.ctas[b] = n.t6_ctas[b];
+    }
+    tp.B = n_scans;
+    tp.w1 = reinterpret_cast<const __nv_bfloat16*>(n.t6_w1);
+    tp.alpha = n.alpha;
+    const int grid = n.t6_ctas[0] + n.t6_ctas[1] + n.t6_ctas[2];
+    if (n.tower_mode == 1) {
+      tp.w2 = reinterpret_cast<const __nv_bfloat16*>(n.convs[1].wt_bf16); tp.b2 = n.convs[1].bias3;
+      tp.out = reinterpret_cast<__nv_bfloat16*>(flat);
+      k6_tower<64, true, 1><<<grid, kT6Threads, T6Smem<64, true>::total, st>>>(tp);
+      RML_CUDA(c, cudaGetLastError());
+      ++c->launches;
+      return RML_OK;
+    }
+    tp.w2 = nullptr; tp.b2 = nullptr;
+    tp.out = reinterpret_cast<__nv_bfloat16*>(ping);
+    k6_tower<128, false, 2><<<grid, kT6Threads, T6Smem<128, false>::total, st>>>(tp);
+    RML_CUDA(c, cudaGetLastError());
+    ++c->launches;
+  }
+  const bool fuse1 = feats && !n.tower_mode && n.use_igemm && n.fuse_resize && (n.convs[0].cout == 64 || n.convs[0].cout == 128);
+  if (feats && !fuse1 && !n.tower_mode) {
     int rc = net_resize(c, feats, n_scans, images, st);
     if (rc) return rc;
   }
@@ -1808,6 +1904,11 @@ static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_
   const void* cur = feats ? images : images_in;
   int hw = n.R;
   size_t l0 = 0;
+  if (n.tower_mode == 2) {
+    cur = ping;
+    hw = (hw + 1) / 2;
+    l0 = 1;
+  }
   if (fuse1) {
     // K3 + first tower layer in one kernel: the resized image never leaves shared memory
     const NetConv& cv = n.convs[0];
