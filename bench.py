@@ -272,7 +272,7 @@ def net_leg(kind, eng_dev, cubes, n_scans, passes, steps, rank, world, dist, str
     dev = cubes.device
     eng = Engine(dev.index)
     spec = onets.random_dnn(0) if kind == "dnn" else onets.random_sgan(0)
-    net = GpuNetClassifier(spec, engine=eng, chunk=int(os.environ.get("RML_BENCH_NET_CHUNK", "2048")))
+    net = GpuNetClassifier(spec, engine=eng, chunk=int(os.environ.get("RML_BENCH_NET_CHUNK", "8192" if kind == "dnn" else "4096")))
     sub = cubes[:n_scans]
     launches0 = eng.launch_count
     out = net.predict_cubes(sub)

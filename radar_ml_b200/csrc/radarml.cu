@@ -134,9 +134,10 @@ struct Net {
   // fused tower kernel (k6_tower.cuh): 0 off, 1 = dnn (resize + layer 1 + layer 2 on chip),
   // 2 = sgan (resize + layer 1 on the tensor cores, NHWC bf16 out)
   int tower_mode = 0;
-  uint16_t* t6_w1 = nullptr;   // [3][C1][32] bf16: whi(9) | whi(9) | wlo(9) | 0(5)
+  uint16_t* t6_w1 = nullptr;   // [3][C1][32] fp16: whi(9), bias hi | whi(9), 0 | wlo(9), bias lo | 0, 0
   float* t6_b1 = nullptr;      // [3][C1]
   int t6_ctas[3] = {0, 0, 0};
+  int t6_dbg = 0;              // RML_T6_DBG timing experiments (results are wrong when set)
 };
 
 }  // namespace
@@ -1726,17 +1727,15 @@ int rml_net_finish(rml_ctx* c) {
   if (n.tower_mode) {
     const NetConv& c0 = n.convs[0];
     const int C1 = c0.cout;
-    auto bf16_rn = [](float v) {
-      uint32_t u;
-      memcpy(&u, &v, 4);
-      u = (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
-      return static_cast<uint16_t>(u);
+    // fp16 hi / lo split (22 bits; fp16 subnormals bound the absolute error by 2^-25)
+    auto f16_bits = [](float v) {
+      const __half_raw r = static_cast<__half_raw>(__float2half_rn(v));
+      return static_cast<uint16_t>(r.x);
     };
-    auto bf16_to_f = [](uint16_t h) {
-      const uint32_t u = static_cast<uint32_t>(h) << 16;
-      float v;
-      memcpy(&v, &u, 4);
-      return v;
+    auto f16_to_f = [](uint16_t b) {
+      __half_raw r;
+      r.x = b;
+      return __half2float(__half(r));
     };
     std::vector<uint16_t> w1(static_cast<size_t>(3) * C1 * kT6K1, 0);
     std::vector<float> b1(static_cast<size_t>(3) * C1);
@@ -1746,18 +1745,19 @@ int rml_net_finish(rml_ctx* c) {
         uint16_t* row = &w1[(static_cast<size_t>(br) * C1 + co) * kT6K1];
         for (int tap = 0; tap < 9; ++tap) {
           const float w = c0.w_host[br][static_cast<size_t>(tap) * C1 + co];     // HWIO with cin = 1
-          const uint16_t hi = bf16_rn(w);
-          const uint16_t lo = bf16_rn(w - bf16_to_f(hi));
-          row[tap] = hi; row[9 + tap] = hi; row[18 + tap] = lo;                  // pairs with A: hi | lo | hi
+          const uint16_t hi = f16_bits(w);
+          const uint16_t lo = f16_bits(w - f16_to_f(hi));
+          row[tap] = hi; row[10 + tap] = hi; row[20 + tap] = lo;                 // pairs with A: hi | lo | hi
         }
-        // the bias rides in the GEMM: A carries 1.0 in columns 27 and 28
-        const uint16_t bhi = bf16_rn(c0.b_host[br][co]);
-        row[27] = bhi;
-        row[28] = bf16_rn(c0.b_host[br][co] - bf16_to_f(bhi));
+        // the bias rides in the GEMM: A carries 1.0 in columns 9 and 29
+        const uint16_t bhi = f16_bits(c0.b_host[br][co]);
+        row[9] = bhi;
+        row[29] = f16_bits(c0.b_host[br][co] - f16_to_f(bhi));
       }
     if ((rc = upload(c, &n.t6_w1, w1.data(), w1.size()))) return rc;
     if ((rc = upload(c, &n.t6_b1, b1.data(), b1.size()))) return rc;
     // persistent CTAs per branch, proportional to the per-image cost (resize rows differ: 22 / 31 / 22)
+    if (const char* e = getenv("RML_T6_DBG")) n.t6_dbg = atoi(e);
     int split[3] = {50, 52, 46};
     if (const char* e = getenv("RML_T6_SPLIT")) sscanf(e, "%d,%d,%d", &split[0], &split[1], &split[2]);
     const int tot = split[0] + split[1] + split[2];
@@ -1775,17 +1775,25 @@ int rml_net_finish(rml_ctx* c) {
 // The conv towers run chunk by chunk (their activations are large); the tcgen05 dense stack runs
 // once per dense group of up to kDenseGroup scans so that it has one tile for every SM.
 constexpr int64_t kDenseGroup = 148 * 128;   // one 128-scan tile per SM: the dense stack fills the chip
-static size_t net_tower_bytes_per_scan(const rml_ctx* c) {
-  const Net& n = c->net;
-  size_t img = static_cast<size_t>(3) * n.R * n.R * 4;
-  size_t act = 0;
+// per-scan bytes of the tower scratch: resized images (only the unfused resize kernel writes them)
+// and the two ping-pong activation buffers (bf16 on the tensor-core path; none at all when the
+// dnn towers run fused on chip)
+static void net_tower_sizes(const Net& n, size_t* img, size_t* act) {
+  *img = n.tower_mode ? 0 : static_cast<size_t>(3) * n.R * n.R * 4;
+  *act = 0;
+  if (n.tower_mode == 1) return;
+  const size_t esz = n.use_igemm ? 2 : 4;
   int hw = n.R;
   for (size_t l = 0; l + 1 < n.convs.size(); ++l) {
     hw = (hw + 1) / 2;
-    size_t a = static_cast<size_t>(3) * hw * hw * n.convs[l].cout * 4;
-    if (a > act) act = a;
+    const size_t a = static_cast<size_t>(3) * hw * hw * n.convs[l].cout * esz;
+    if (a > *act) *act = a;
   }
-  return img + 2 * act;
+}
+static size_t net_tower_bytes_per_scan(const rml_ctx* c) {
+  size_t img, act;
+  net_tower_sizes(c->net, &img, &act);
+  return img + 2 * act + 64;
 }
 struct NetPlan {
   int64_t chunk = 0, group = 0;
@@ -1851,16 +1859,9 @@ static int net_resize(rml_ctx* c, const float* feats, int64_t n_scans, float* im
 static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_in, int64_t n_scans,
                             char* ws, uint16_t* flat, cudaStream_t st) {
   Net& n = c->net;
-  size_t img_b = align256(static_cast<size_t>(n_scans) * 3 * n.R * n.R * 4);
-  size_t act = 0;
-  {
-    int hw = n.R;
-    for (size_t l = 0; l + 1 < n.convs.size(); ++l) {
-      hw = (hw + 1) / 2;
-      size_t a = static_cast<size_t>(3) * hw * hw * n.convs[l].cout * 4;
-      if (a > act) act = a;
-    }
-  }
+  size_t img1, act;
+  net_tower_sizes(n, &img1, &act);
+  size_t img_b = align256(img1 * static_cast<size_t>(n_scans));
   size_t act_b = align256(act * static_cast<size_t>(n_scans));
   float* images = reinterpret_cast<float*>(ws);
   float* ping = reinterpret_cast<float*>(ws + img_b);
@@ -1878,8 +1879,9 @@ static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_
       tp.ctas[b] = n.t6_ctas[b];
     }
     tp.B = n_scans;
-    tp.w1 = reinterpret_cast<const __nv_bfloat16*>(n.t6_w1);
+    tp.w1 = reinterpret_cast<const __half*>(n.t6_w1);
     tp.alpha = n.alpha;
+    tp.dbg = n.t6_dbg;
     const int grid = n.t6_ctas[0] + n.t6_ctas[1] + n.t6_ctas[2];
     if (n.tower_mode == 1) {
       tp.w2 = reinterpret_cast<const __nv_bfloat16*>(n.convs[1].wt_bf16); tp.b2 = n.convs[1].bias3;

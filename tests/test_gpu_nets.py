@@ -73,10 +73,7 @@ def test_forward_matches_oracle(eng, kind):
     slack = 2e-3 * np.abs(t_ref).max() if igemm else 1e-5
     ulp = np.abs(t_ref) * 2.0 ** -7 + slack
     assert (np.abs(t_gpu - t_ref) <= ulp).all()
-    # (the first layer runs on the tensor cores as a two-term bf16 split of the fp32 image and kernel,
-    #  ~2^-17 relative instead of fp32's 2^-24: a few more values land on the other side of a bf16
-    #  rounding boundary than with an fp32 first layer, and three layers deep that is ~3 % for sgan)
-    assert (t_gpu != nets.bf16_round(t_ref).reshape(t_gpu.shape)).mean() < (4e-2 if igemm else 1e-3)
+    assert (t_gpu != nets.bf16_round(t_ref).reshape(t_gpu.shape)).mean() < (2e-2 if igemm else 1e-3)
     # (2) tcgen05 dense stack + head: 1e-5 against float64 on the very operands it consumed
     P_t, lg_t = nets.dense_from_tower(spec, t_gpu)
     assert np.abs(proba.cpu().numpy()[:, :P_t.shape[1]].astype(np.float64) - P_t).max() < TOL
