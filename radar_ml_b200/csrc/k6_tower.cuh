@@ -433,16 +433,20 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
           const uint32_t taddr = tmem1 + (static_cast<uint32_t>(q * 32) << 16);
           unsigned char* dst_row = nullptr;
           uint32_t sw = 0;
-          __nv_bfloat16* gout = nullptr;
           if (FUSE2) {
             const int py = r & 1, a = r >> 1, px = x1 & 1, j = x1 >> 1;
             const int slot = (py ? (px ? kSlot11 : kSlot10) : (px ? kSlot01 : 0)) + a * kT6Pitch + j;
             dst_row = strip + slot * 128;
             sw = slot & 7;                      // the swizzle follows the absolute address (strip is 1024-aligned)
-          } else {
-            gout = p.out + ((static_cast<int64_t>(b) * 3 + br) * H1 * H1 + static_cast<int64_t>(y1) * H1 + x1) * C1;
           }
           const bool store = pidx < kPixPerStrip && (FUSE2 || y1 < H1);
+          // !FUSE2: a thread holds one pixel's channels, so a direct store would touch 32 half-filled
+          // sectors per instruction (measured: 141 k cycles per image, the whole kernel).  The warp
+          // transposes each 32-pixel x 64-byte block through its quarter of the group's im2col tile
+          // (free once the layer-1 MMAs have retired) and writes 64 contiguous bytes per 4 lanes.
+          unsigned char* stg = a1 + grp * kT6A1Bytes + q * 2048;
+          __nv_bfloat16* gtile = p.out + ((static_cast<int64_t>(b) * 3 + br) * H1 * H1 +
+                                          static_cast<int64_t>(y1_0) * H1 + grp * 128 + q * 32) * C1;
 #pragma unroll
           for (int c0 = 0; c0 < C1; c0 += 32) {
             uint32_t v[32];
@@ -452,13 +456,28 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
 #pragma unroll
             for (int e = 0; e < 32; e += 2)
               pk[e >> 1] = act_pack<ACT>(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), p.alpha);
-            if (store) {
+            if (FUSE2) {
+              if (store) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const uint4 w = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                if (FUSE2) *reinterpret_cast<uint4*>(dst_row + ((((c0 >> 3) + c) ^ sw) << 4)) = w;
-                else *reinterpret_cast<uint4*>(gout + c0 + 8 * c) = w;
+                for (int c = 0; c < 4; ++c)
+                  *reinterpret_cast<uint4*>(dst_row + ((((c0 >> 3) + c) ^ sw) << 4)) =
+                      make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
               }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(stg + lane * 64 + (((c ^ (lane >> 1)) & 3) << 4)) =
+                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int px = 8 * i + (lane >> 2), c = lane & 3;
+                const uint4 w = *reinterpret_cast<const uint4*>(stg + px * 64 + (((c ^ (px >> 1)) & 3) << 4));
+                const int pp = grp * 128 + q * 32 + px;                  // pixel inside the round
+                if (pp < kPixPerStrip && y1_0 + pp / H1 < H1)
+                  *reinterpret_cast<uint4*>(gtile + static_cast<int64_t>(px) * C1 + c0 + 8 * c) = w;
+              }
+              __syncwarp();
             }
           }
         }
