@@ -77,7 +77,11 @@ struct T6Smem {
   static constexpr int w1 = a1 + 4 * kT6A1Bytes;                         // [C1][32] fp16 no-swizzle K-major
   static constexpr int w2 = (w1 + C1 * kT6K1 * 2 + 1023) & ~1023;        // FUSE2: 9 taps x [C2][64] bf16, SW128
   static constexpr int strip = w2 + (FUSE2 ? 9 * C2 * 128 : 0);          // FUSE2: 4 parity planes + tail
-  static constexpr int plane0_slots = (kT6TH + 1) * kT6Pitch, plane1_slots = kT6TH * kT6Pitch;
+  // plane sizes padded so that the even- and odd-column planes of a row parity start 4 slots apart
+  // modulo 8: the 128-bit stores of a quarter-warp (4 even + 4 odd pixels) then hit 8 distinct bank
+  // groups under the 128B swizzle (unpadded they collided two ways: 1 380 extra wavefronts per image)
+  static constexpr int plane0_slots = ((kT6TH + 1) * kT6Pitch + 7) / 8 * 8 + 4, plane1_slots = (kT6TH * kT6Pitch + 7) / 8 * 8 - 4;
+  static_assert(plane0_slots >= (kT6TH + 1) * kT6Pitch && plane1_slots >= kT6TH * kT6Pitch && plane0_slots % 8 == 4 && plane1_slots % 8 == 4, "plane padding");
   static constexpr int strip_slots = 2 * plane0_slots + 2 * plane1_slots + 24;     // tail: the last tile over-reads
   static constexpr int tabs = strip + (FUSE2 ? strip_slots * 128 : 0);   // kh [R][12] | kv [R][8] f64, bh | bv [R] int2
   static constexpr int tabs_bytes = R * (12 + 8) * 8 + 2 * R * 8;
@@ -123,7 +127,7 @@ __device__ __forceinline__ void t6_pass_h(int rt, const float* src, double* tmpT
   const int2 bd = s_bh[xx];
   double k[KT];
 #pragma unroll
-  for (int x = 0; x < KT; ++x) k[x] = x < bd.y ? s_kh[xx * 12 + x] : 0.0;
+  for (int x = 0; x < KT; ++x) k[x] = x < bd.y ? s_kh[x * R + xx] : 0.0;      // [tap][column]: lanes read neighbours
   double* out = tmpT + xx * kT6HP;          // transposed: the vertical pass walks a column contiguously
   for (int y = g; y < H; y += 2 * groups) {
     const int y2 = y + groups;
@@ -156,7 +160,7 @@ __device__ __forceinline__ void t6_pass_v(int rt, const double* tmpT, float* img
   const int2 bd = s_bv[yy];
   double k[KT];
 #pragma unroll
-  for (int y = 0; y < KT; ++y) k[y] = y < bd.y ? s_kv[yy * 8 + y] : 0.0;
+  for (int y = 0; y < KT; ++y) k[y] = y < bd.y ? s_kv[y * R + yy] : 0.0;      // [tap][row]: lanes read neighbours
   float* orow = img + yy * P;
   for (int xx = cg; xx < R; xx += 2 * kCg) {
     const int xx2 = xx + kCg;
@@ -206,8 +210,8 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
   unsigned char* w1s = smem + L::w1;
   unsigned char* w2s = smem + L::w2;
   unsigned char* strip = smem + L::strip;
-  double* s_kh = reinterpret_cast<double*>(smem + L::tabs);            // [R][12]
-  double* s_kv = s_kh + R * 12;                                         // [R][8]
+  double* s_kh = reinterpret_cast<double*>(smem + L::tabs);            // [12][R] (tap-major)
+  double* s_kv = s_kh + R * 12;                                         // [8][R]
   int2* s_bh = reinterpret_cast<int2*>(s_kv + R * 8);
   int2* s_bv = s_bh + R;
   float* s_b2 = reinterpret_cast<float*>(smem + L::bias);
@@ -239,8 +243,8 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
   {
     const double* kh = p.rz.kh[br];
     const double* kv = p.rz.kv[br];
-    for (int e = tid; e < R * 12; e += kT6Threads) { const int xx = e / 12, x = e - xx * 12; s_kh[e] = x < ksh ? kh[xx * ksh + x] : 0.0; }
-    for (int e = tid; e < R * 8; e += kT6Threads) { const int yy = e >> 3, y = e & 7; s_kv[e] = y < ksv ? kv[yy * ksv + y] : 0.0; }
+    for (int e = tid; e < R * 12; e += kT6Threads) { const int x = e / R, xx = e - x * R; s_kh[e] = x < ksh ? kh[xx * ksh + x] : 0.0; }
+    for (int e = tid; e < R * 8; e += kT6Threads) { const int y = e / R, yy = e - y * R; s_kv[e] = y < ksv ? kv[yy * ksv + y] : 0.0; }
     for (int e = tid; e < R; e += kT6Threads) { s_bh[e] = p.rz.bh[br][e]; s_bv[e] = p.rz.bv[br][e]; }
   }
   if (FUSE2) {
