@@ -68,7 +68,8 @@ struct TowerParams {
   const __nv_bfloat16* w2;       // FUSE2: [3][C2][9*64] bf16, K = tap*64 + ci (k4_conv_igemm layout)
   const float* b2;               // FUSE2: [3][C2]
   float alpha;                   // LeakyReLU slope (ACT == 2)
-  int dbg;                       // experiments only (RML_T6_DBG): 64 = strided-column horizontal pass (same results);
+  int dbg;                       // experiments only (RML_T6_DBG): 64 = strided-column horizontal pass, 32 = gather after
+                                 // the layer-1 commit (same results);
                                  // 1 no layer-2 MMAs, 2 no resize, 4 no layer-1
                                  // epilogue, 8 no im2col, 16 no layer-1 MMAs — results are wrong with any bit set
   __nv_bfloat16* out;            // FUSE2: [B][3][H2][H2][C2]; else [B*3][H1][H1][C1]
@@ -346,10 +347,9 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
       float* img = ibuf ? img_alt : img_main;
       for (int k = 0; k < NB; ++k) {
         if (iuse > 0) {
-          // the T role is done with this block of the image that was here before: one warp polls, the
-          // others park on the hardware barrier (a parked warp costs no issue slots, a polling one does)
-          if (rt < 32) mbar_wait_relaxed(&empty[ibuf * NB + k], (iuse - 1) & 1);
-          bar_group(6, kT6RThreads);
+          // the T role is done with this block of the image that was here before (two image buffers:
+          // normally long ago)
+          mbar_wait_relaxed(&empty[ibuf * NB + k], (iuse - 1) & 1);
         }
         const int lo = blk_lo(k), hi = blk_hi(k);
         if (p.images) {
@@ -418,7 +418,6 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
       // work, the 44 UMMAs of a round — one thread, ~2.5 k cycles — made group 0 the straggler at every
       // barrier: half of the tile role's time was barrier wait.)
       const bool mma_warp = warp == kT6TThreads / 32 - 1;
-      const int gthreads = grp == 3 ? 96 : 128;                    // group barrier without the issuer
       const int pidx = grp * 128 + m;                               // pixel of this thread inside a round
       const int prow = pidx / H1, x1 = pidx - prow * H1;
       const bool store = pidx < kPixPerStrip;
@@ -427,14 +426,16 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
       unsigned char* dst_row = strip + slot * 128;
       const uint32_t sw = slot & 7;             // the swizzle follows the absolute address (strip is 1024-aligned)
       const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-      const uint32_t tmemA0 = tmem_base + 4 * C1 + 64;              // four A tiles of 16 columns
+      const uint32_t tmemA0 = tmem_base + 4 * C1 + 64;              // 2 x four A tiles of 16 columns (double-buffered)
+      const bool early = !(p.dbg & 32);         // gather round r+1 BEFORE awaiting the layer-1 commit of round r
       auto im2col = [&](uint32_t r) {
         const uint32_t im = r / NB;
         const int s = static_cast<int>(r - im * NB);
         // image rows of this round are in smem (acquire); one warp of the group polls, the rest park
         const uint32_t ibuf = im % NIMG, iuse = im / NIMG;
-        if (q == 0) mbar_wait_relaxed(&full[ibuf * NB + s], iuse & 1);
-        bar_group(1 + grp, gthreads);
+        // every warp acquires the barrier itself: it has normally completed long ago (the R role runs
+        // ahead), and a group barrier behind one polling warp costs a round trip per round
+        mbar_wait_relaxed(&full[ibuf * NB + s], iuse & 1);
         if (!warp_dead && !(p.dbg & 8)) {
           const int y1 = 2 * kT6TH * s + prow;
           const bool live = store && y1 < H1;                       // y1 == H1 is layer 2's zero pad row
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
           // shared-memory store and no shared-memory read
           const uint32_t av[16] = {hw[0], hw[1], hw[2], hw[3], hw[4], lw[0], lw[1], lw[2],
                                    lw[3], lw[4], hw[0], hw[1], hw[2], hw[3], hw[4], 0u};
-          tmem_st_32x16(tmemA0 + grp * 16 + lane_off, av);
+          tmem_st_32x16(tmemA0 + (r & 1) * 64 + grp * 16 + lane_off, av);
           tmem_st_wait();
         }
         // this warp no longer reads the previous block of image rows (and, in the last round, this one)
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
               for (int g = 0; g < 4; ++g)
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
-                  umma_f16_ts(tmem_base + g * C1, tmemA0 + g * 16 + 8 * k, t6_desc_noswz(b_addr + k * 256), idesc1, k != 0);
+                  umma_f16_ts(tmem_base + g * C1, tmemA0 + (r & 1) * 64 + g * 16 + 8 * k, t6_desc_noswz(b_addr + k * 256), idesc1, k != 0);
             }
             if (r < n_rounds) umma_commit(&mbar1[0]);
             if (r >= 1) {
@@ -518,6 +519,9 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
           __syncwarp();
           continue;
         }
+        // the im2col tiles are double-buffered in tensor memory, so the gather of round r+1 does not wait
+        // for the layer-1 UMMAs of round r: it hides their commit -> mbarrier round trip
+        if (early && r + 1 < n_rounds) im2col(r + 1);
         // group 0 drains strip r-2 (its UMMAs were awaited by every warp in iteration r-1)
         if (grp == 0 && r >= 2) {
           const uint32_t rr = r - 2, im = rr / NB;
@@ -539,11 +543,10 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
           }
           tc_fence_before();
         }
-        if (r + 1 < n_rounds) im2col(r + 1);
+        if (!early && r + 1 < n_rounds) im2col(r + 1);
         if (r >= 1) {
           // the strip planes are still being read by the layer-2 UMMAs of round r-1
-          if (q == 0) mbar_wait_relaxed(mbar2, (r - 1) & 1);
-          bar_group(1 + grp, gthreads);
+          mbar_wait_relaxed(mbar2, (r - 1) & 1);
         }
         if (r < n_rounds) {
           if (store && !warp_dead && !(p.dbg & 4)) {
