@@ -8,7 +8,8 @@
 //               registers, the per-row max over k (xy) is one CREDUX.MAX.F32 per row
 //   warps 8..11 "column" warps: every 4th slab each, max over j for every k (xz)
 //   warp 12     producer: issues the bulk copies (one elected lane)
-//   warp 13     flusher: writes the finished feature row back (bulk S2G for u8)
+//   warp 13     flusher: writes the finished u8 feature row back (bulk S2G); float32 rows are stored
+//               straight from the row / column warps (coalesced float2 segments), no staging
 // One HBM read of the cube, no re-reads; output is 2 % (u8) / 8 % (f32) of the input bytes.
 #pragma once
 #include <cfloat>
@@ -26,10 +27,15 @@ constexpr int kCubeElems = kSX * kSlabElems;       // 120032
 constexpr int kFxz = kSX * kSZ, kFyz = kSY * kSZ, kFxy = kSX * kSY;  // 3872, 5456, 682
 constexpr int kRowWarps = 8, kColWarps = 4;
 constexpr int kK1Threads = (kRowWarps + kColWarps + 2) * 32;  // 448
-// ring depth: 8 slabs (175 KB in flight) for the u8 path, 4 for f32 (its staging rows are 4x larger)
+// ring depth: 8 slabs (175 KB in flight per SM).  u8 rows are staged in shared memory (one bulk store
+// per scan, the co-resident scorer is told when it has landed); float32 rows go STRAIGHT to global
+// memory from the warps that produce them — every store is a coalesced float2 row segment — so they
+// need no staging and the ring keeps its full depth (with two 40 KB staging rows it had 4 stages and
+// the kernel was latency-bound at 6.1 TB/s).
 template <typename OutT>
 struct K1Cfg {
-  static constexpr int kStages = sizeof(OutT) == 1 ? 8 : 4;
+  static constexpr int kStages = 8;
+  static constexpr bool kDirect = sizeof(OutT) == 4;
 };
 // A column warp only waits on the `full` barriers of the slabs it owns, so it must also own the
 // previous use of that ring slot (mbarrier parity waits cannot tell phase n from phase n-2).
@@ -119,7 +125,7 @@ __host__ __device__ constexpr int k1_staging_bytes() {
 }
 template <typename OutT>
 __host__ __device__ constexpr int k1_smem_bytes() {
-  return K1Cfg<OutT>::kStages * kSlabBytes + 2 * k1_staging_bytes<OutT>() + 256;
+  return K1Cfg<OutT>::kStages * kSlabBytes + (K1Cfg<OutT>::kDirect ? 0 : 2 * k1_staging_bytes<OutT>()) + 256;
 }
 
 // Row-warp role of k1_project_max: NR rows j of every slab (NR compile-time so the 12 smem
@@ -144,8 +150,13 @@ __device__ __forceinline__ void k1_row_warp(const K1Params& p, const float* slab
   const bool third = lane < 24;
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++t) {
     const int buf = t & 1;
-    OutT* stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
-    mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
+    OutT* stg;
+    if (K1Cfg<OutT>::kDirect) {
+      stg = reinterpret_cast<OutT*>(p.feats) + b * static_cast<int64_t>(p.stride);   // the global row itself
+    } else {
+      stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
+      mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
+    }
     for (int i = 0; i < kSX; ++i, ++it) {
       const int stage = it % kK1Stages;
       mbar_wait(&full[stage], (it / kK1Stages) & 1);
@@ -196,9 +207,11 @@ __device__ __forceinline__ void k1_row_warp(const K1Params& p, const float* slab
       if (lane == 0 && tot) atomicAdd(&norm_acc[buf], tot);
       sumsq = 0;
     }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&done[buf]);
+    if (!K1Cfg<OutT>::kDirect) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&done[buf]);
+    }
   }
   if (bad) atomicAdd(p.status, 1u);
 }
@@ -210,7 +223,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
   float* slabs = reinterpret_cast<float*>(smem);
   OutT* stg0 = reinterpret_cast<OutT*>(smem + kK1Stages * kSlabBytes);
   constexpr int kStgBytes = k1_staging_bytes<OutT>();
-  unsigned char* tail = smem + kK1Stages * kSlabBytes + 2 * kStgBytes;
+  unsigned char* tail = smem + kK1Stages * kSlabBytes + (K1Cfg<OutT>::kDirect ? 0 : 2 * kStgBytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);   // [kK1Stages]
   uint64_t* empty = full + kK1Stages;                   // [kK1Stages]
   uint64_t* done = empty + kK1Stages;                   // [2] scan finished in staging buf
@@ -233,8 +246,9 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
     fence_barrier_init();
   }
   // zero both staging rows once: pad bytes [F, stride) stay zero for the whole kernel
-  for (int i = threadIdx.x; i < 2 * kStgBytes / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(stg0)[i] = 0u;
+  if (!K1Cfg<OutT>::kDirect)
+    for (int i = threadIdx.x; i < 2 * kStgBytes / 4; i += blockDim.x)
+      reinterpret_cast<uint32_t*>(stg0)[i] = 0u;
   __syncthreads();
 
   const int off_xz = 0;
@@ -255,8 +269,13 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
     uint32_t sumsq = 0, bad = 0;
     for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++t) {
       const int buf = t & 1;
-      OutT* stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
-      mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
+      OutT* stg;
+      if (K1Cfg<OutT>::kDirect) {
+        stg = reinterpret_cast<OutT*>(p.feats) + b * static_cast<int64_t>(p.stride);
+      } else {
+        stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
+        mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
+      }
       for (int i = 0; i < kSX; ++i, ++it) {
         if ((it % kColWarps) != static_cast<uint32_t>(c)) continue;   // ownership follows the ring slot
         const int stage = it % kK1Stages;
@@ -291,9 +310,11 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
         if (lane == 0 && tot) atomicAdd(&norm_acc[buf], tot);
         sumsq = 0;
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&done[buf]);
+      if (!K1Cfg<OutT>::kDirect) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[buf]);
+      }
     }
     if (bad) atomicAdd(p.status, 1u);
   } else if (warp == kRowWarps + kColWarps) {
@@ -313,8 +334,8 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
         }
       }
     }
-  } else {
-    // ------------------------------------------------------------------ flusher
+  } else if (!K1Cfg<OutT>::kDirect) {
+    // ------------------------------------------------------------------ flusher (u8 rows)
     for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++t) {
       const int buf = t & 1;
       OutT* stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
@@ -333,14 +354,6 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
             atomicAdd(&p.tile_done[b >> 7], 1u);
           }
         }
-      } else {
-        // (n,F) float32 rows are only 8-byte aligned (F*4 = 40040): plain coalesced stores
-        float* out = reinterpret_cast<float*>(p.feats) + b * static_cast<int64_t>(p.stride);
-        const float* src = reinterpret_cast<const float*>(stg);
-        for (int idx = 2 * lane; idx < p.F; idx += 64)
-          *reinterpret_cast<float2*>(out + idx) = *reinterpret_cast<const float2*>(src + idx);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sfree[buf]);
       }
     }
     if (sizeof(OutT) == 1 && lane == 0) bulk_wait_all<0>();
