@@ -602,6 +602,36 @@ def run_ours(args):
             latency["reference_loop_one_core"] = lat1
             eng.load_model(params)
 
+    # ---- DerivedTarget axis sums (common.py:45-80) inside K1's single pass
+    derived = None
+    if rank == 0 and world == 1:
+        from radar_ml_b200._lib import U8 as _U8
+        nd = min(16384, B)
+        cd = cubes[:nd]
+
+        def ev_ms(fn, reps=5):
+            fn()
+            torch.cuda.synchronize(dev)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(reps):
+                fn()
+            a1.record(stream)
+            torch.cuda.synchronize(dev)
+            return a0.elapsed_time(a1) / reps
+        t_proj = ev_ms(lambda: eng.project(cd, dtype=_U8))
+        t_der = ev_ms(lambda: eng.derive_targets(cd, num_targets=3))
+        t_one = ev_ms(lambda: eng.project_derive(cd, num_targets=3, dtype=_U8))
+        _, _, ijk_f, sums_f = eng.project_derive(cd[:64], num_targets=3, dtype=_U8, want_sums=True)
+        c64 = cd[:64].cpu().numpy().astype(np.float64)
+        want = np.concatenate([c64.sum(axis=(2, 3)), c64.sum(axis=(1, 3)), c64.sum(axis=(1, 2))], axis=1)
+        peak_d, _ = measured_peaks()
+        derived = {"workload": "%d cubes: MAX projections (u8 rows) + DerivedTarget axis sums and top-3 indices" % nd,
+                   "two_passes_ms": t_proj + t_der, "project_ms": t_proj, "derive_targets_ms": t_der,
+                   "one_pass_ms": t_one, "one_pass_hbm_frac": nd * CUBE_BYTES / t_one / 1e6 / peak_d,
+                   "sums_equal_numpy": bool(np.array_equal(sums_f.cpu().numpy().astype(np.float64), want)),
+                   "ijk_equal_separate_kernel": bool(torch.equal(ijk_f, eng.derive_targets(cd[:64], num_targets=3)))}
+
     # ---- general-precision case: real-valued cubes + non-integral support vectors
     general = None
     if rank == 0 and world == 1:
@@ -762,6 +792,8 @@ def run_ours(args):
             line["latency"] = latency
         if general:
             line["general_precision"] = general
+        if derived:
+            line["derived_targets"] = derived
         if u8leg:
             line["u8_cubes"] = u8leg
         if shard:

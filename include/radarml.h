@@ -126,6 +126,15 @@ int rml_matrix_indices(rml_ctx* ctx, const double* xyz_dev, int64_t B, int32_t* 
  * sums_dev (nullable) float32 [B][sx+sy+sz] = theta | phi | r sums. */
 int rml_derive_targets(rml_ctx* ctx, const float* cubes_dev, int64_t B, int num_targets,
                        int32_t* ijk_dev, float* sums_dev, rml_stream stream);
+/* rml_project(RML_MODE_MAX) and rml_derive_targets in ONE pass over the cubes ("the
+ * axis sums can share K1's single HBM pass"): the projection kernel's row warps accumulate the theta /
+ * phi / r sums from the voxels they already hold in registers, its flusher warp ranks them.  Same
+ * outputs as the two separate calls (identical for integer-valued cubes; for real-valued cubes the
+ * float32 sums differ in the last bits because the summation order differs).  Default arena; other
+ * arenas run the two kernels back to back. */
+int rml_project_derive(rml_ctx* ctx, const float* cubes_dev, int64_t B, uint32_t mask, int dtype,
+                       void* feats_dev, int32_t* norms_dev, int num_targets, int32_t* ijk_dev,
+                       float* sums_dev, rml_stream stream);
 /* common.py:143-144 scipy.ndimage.zoom(p, proj_zoom[i]) (order-3 spline) for arenas that differ
  * from the training arena (predict.py:34-54, README.md:207).  For fixed sizes the zoom is a
  * separable linear operator: a_rows [out_h][in_h], a_cols [out_w][in_w] (HOST float64,

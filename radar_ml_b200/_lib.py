@@ -86,6 +86,7 @@ SIGNATURES = {
     "rml_load_linear": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _f64]),
     "rml_model_is_integral": (C.c_int, [_vp]),
     "rml_project": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _u32, C.c_int, _vp, _vp, _vp]),
+    "rml_project_derive": (C.c_int, [_vp, _vp, _i64, _u32, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "rml_process_samples": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _u32, C.c_int, _vp, _vp]),
     "rml_matrix_indices": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "rml_derive_targets": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp]),

@@ -101,9 +101,11 @@ __global__ void __launch_bounds__(256) k0_derive_targets(const DeriveParams p) {
       }
     }
     __syncthreads();
-    if (p.sums)
+    if (p.sums) {
       for (int e = threadIdx.x; e < p.sx + p.sy + p.sz; e += blockDim.x)
         p.sums[b * (p.sx + p.sy + p.sz) + e] = ds[e];
+      __syncthreads();      // the ranking below overwrites the winners with -FLT_MAX
+    }
     // top-T per axis: warp a (0..2) repeatedly takes the arg-max of its axis
     if (warp < 3) {
       float* S = warp == 0 ? Sx : (warp == 1 ? Sy : Sz);

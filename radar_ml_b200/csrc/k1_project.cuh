@@ -58,7 +58,18 @@ struct K1Params {
   int split;                // bulk copies per slab (1; 2 / 4 are tuning experiments)
   unsigned int* tile_done;  // nullable: [ceil(B/128)] += 1 per finished scan (u8 path) so a
                             // co-resident scorer can start on a 128-scan tile as soon as it is whole
+  // SUMS variant (common.py:45-80 DerivedTarget.get_derived_targets in the SAME pass over the cube):
+  int32_t* dt_ijk;          // [B][dt_T][3], ascending by axis sum like np.argsort (last = strongest)
+  float* dt_sums;           // nullable: [B][22 + 31 + 176] theta | phi | r axis sums
+  int dt_T;
 };
+
+constexpr int kK1MaxTargets = 8;
+// shared memory of the SUMS variant, in floats, per staging parity: per-slab theta partials of the 8 row
+// warps | phi sums | per-warp r partials; plus one final theta | phi | r array for the ranking
+constexpr int kK1SumXs = kSX * kRowWarps, kK1SumSy = 32, kK1SumZp = kRowWarps * kSZ;
+constexpr int kK1SumBuf = kK1SumXs + kK1SumSy + kK1SumZp;
+constexpr int kK1SumFloats = 2 * kK1SumBuf + 232;
 
 // np.max propagates NaN; fmaxf drops it.  max.NaN.f32 (FMNMX.NAN) costs the same instruction.
 __device__ __forceinline__ float max_nan(float a, float b) {
@@ -123,17 +134,24 @@ __host__ __device__ constexpr int k1_staging_bytes() {
   // u8: K-padded row (10112 B for the full mask); f32: 10010*4 rounded up to 128
   return sizeof(OutT) == 1 ? 10112 : 40064;
 }
-template <typename OutT>
+template <typename OutT, bool SUMS = false>
 __host__ __device__ constexpr int k1_smem_bytes() {
-  return K1Cfg<OutT>::kStages * kSlabBytes + (K1Cfg<OutT>::kDirect ? 0 : 2 * k1_staging_bytes<OutT>()) + 256;
+  return K1Cfg<OutT>::kStages * kSlabBytes + (K1Cfg<OutT>::kDirect ? 0 : 2 * k1_staging_bytes<OutT>()) + 256 +
+         (SUMS ? kK1SumFloats * 4 : 0);
+}
+__device__ __forceinline__ float warp_sum_f32(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
 // Row-warp role of k1_project_max: NR rows j of every slab (NR compile-time so the 12 smem
 // loads of a slab are issued back to back and the NR warp reductions overlap).
-template <typename OutT, int NR>
+template <typename OutT, int NR, bool SUMS>
 __device__ __forceinline__ void k1_row_warp(const K1Params& p, const float* slabs, OutT* stg0,
                                             uint64_t* full, uint64_t* empty, uint64_t* done,
-                                            uint64_t* sfree, uint32_t* norm_acc, int warp, int lane) {
+                                            uint64_t* sfree, uint32_t* norm_acc, float* sums_s, int warp, int lane) {
+  constexpr bool kSync = !K1Cfg<OutT>::kDirect || SUMS;     // the flusher has work per scan
   constexpr int kStgBytes = k1_staging_bytes<OutT>();
   constexpr int kK1Stages = K1Cfg<OutT>::kStages;
   const float NEG = -FLT_MAX;
@@ -151,11 +169,16 @@ __device__ __forceinline__ void k1_row_warp(const K1Params& p, const float* slab
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++t) {
     const int buf = t & 1;
     OutT* stg;
-    if (K1Cfg<OutT>::kDirect) {
-      stg = reinterpret_cast<OutT*>(p.feats) + b * static_cast<int64_t>(p.stride);   // the global row itself
-    } else {
-      stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
-      mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
+    if (K1Cfg<OutT>::kDirect) stg = reinterpret_cast<OutT*>(p.feats) + b * static_cast<int64_t>(p.stride);   // the global row itself
+    else stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
+    if (kSync) mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
+    float* sb = sums_s + buf * kK1SumBuf;           // SUMS: this parity's partial-sum area
+    float ysum[NR], zs[6];
+    if (SUMS) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) ysum[r] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) zs[q] = 0.f;
     }
     for (int i = 0; i < kSX; ++i, ++it) {
       const int stage = it % kK1Stages;
@@ -181,6 +204,22 @@ __device__ __forceinline__ void k1_row_warp(const K1Params& p, const float* slab
       }
 #pragma unroll
       for (int r = 0; r < NR; ++r) m[r] = warp_max_nan_f32(m[r]);
+      if (SUMS) {
+        // axis sums of the raw cube from the values already in registers: phi (per row j, over i and
+        // k) and r (per k, over i and j) stay per-lane partials until the end of the scan; theta (per
+        // slab i) is reduced here and left for the flusher, one partial per row warp
+        float xs = 0.f;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const float ex = third ? e[r].x : 0.f, ey = third ? e[r].y : 0.f;
+          const float s6 = ((a[r].x + a[r].y) + (c[r].x + c[r].y)) + (ex + ey);
+          ysum[r] += s6;
+          xs += s6;
+          zs[0] += a[r].x; zs[1] += a[r].y; zs[2] += c[r].x; zs[3] += c[r].y; zs[4] += ex; zs[5] += ey;
+        }
+        xs = warp_sum_f32(xs);
+        if (lane == 0) sb[i * kRowWarps + warp] = xs;
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);    // the slab has been consumed
       // lane r stores the xy value of row r: one conversion per slab instead of NR
@@ -207,8 +246,19 @@ __device__ __forceinline__ void k1_row_warp(const K1Params& p, const float* slab
       if (lane == 0 && tot) atomicAdd(&norm_acc[buf], tot);
       sumsq = 0;
     }
-    if (!K1Cfg<OutT>::kDirect) {
-      fence_proxy_async_smem();
+    if (SUMS) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const float y = warp_sum_f32(ysum[r]);
+        if (lane == 0) sb[kK1SumXs + j0 + r] = y;
+      }
+      float* zp = sb + kK1SumXs + kK1SumSy + warp * kSZ + 2 * lane;
+      *reinterpret_cast<float2*>(zp) = make_float2(zs[0], zs[1]);
+      *reinterpret_cast<float2*>(zp + 64) = make_float2(zs[2], zs[3]);
+      if (third) *reinterpret_cast<float2*>(zp + 128) = make_float2(zs[4], zs[5]);
+    }
+    if (kSync) {
+      if (!K1Cfg<OutT>::kDirect) fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&done[buf]);
     }
@@ -216,8 +266,59 @@ __device__ __forceinline__ void k1_row_warp(const K1Params& p, const float* slab
   if (bad) atomicAdd(p.status, 1u);
 }
 
-template <typename OutT>
+// SUMS: the flusher turns the partial sums of one scan into DerivedTarget's output (common.py:45-80):
+// theta | phi | r axis sums (fixed summation order: reproducible) and, per axis, the dt_T indices with
+// the largest sums, ascending like np.argsort (same ranking rules as k0_derive_targets).
+__device__ __forceinline__ void k1_rank_targets(const K1Params& p, const float* sb, float* S, int64_t b, int lane) {
+  constexpr int kN = kSX + kSY + kSZ;
+  for (int e = lane; e < kN; e += 32) {
+    float v = 0.f;
+    if (e < kSX) {
+#pragma unroll
+      for (int w = 0; w < kRowWarps; ++w) v += sb[e * kRowWarps + w];
+    } else if (e < kSX + kSY) {
+      v = sb[kK1SumXs + e - kSX];
+    } else {
+#pragma unroll
+      for (int w = 0; w < kRowWarps; ++w) v += sb[kK1SumXs + kK1SumSy + w * kSZ + e - kSX - kSY];
+    }
+    S[e] = v;
+    if (p.dt_sums) p.dt_sums[b * kN + e] = v;
+  }
+  __syncwarp();
+  for (int axis = 0; axis < 3; ++axis) {
+    float* A = axis == 0 ? S : (axis == 1 ? S + kSX : S + kSX + kSY);
+    const int n = axis == 0 ? kSX : (axis == 1 ? kSY : kSZ);
+    for (int t = 0; t < p.dt_T; ++t) {
+      float best = -FLT_MAX;
+      int bi = 0x7fffffff;
+      for (int e = lane; e < n; e += 32) {
+        const float v = A[e];
+        if (v > best) { best = v; bi = e; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        if (bi >= n) {     // NaN / -inf sums: lowest unused index, reported (status[3] -> RML_E_INVALID)
+          bi = 0;
+          while (bi < n - 1 && A[bi] == -FLT_MAX) ++bi;
+          if (p.status) atomicAdd(p.status + 3, 1u);
+        }
+        p.dt_ijk[(b * p.dt_T + (p.dt_T - 1 - t)) * 3 + axis] = bi;
+        A[bi] = -FLT_MAX;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <typename OutT, bool SUMS = false>
 __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p) {
+  constexpr bool kSync = !K1Cfg<OutT>::kDirect || SUMS;
   constexpr int kK1Stages = K1Cfg<OutT>::kStages;
   extern __shared__ __align__(128) unsigned char smem[];
   float* slabs = reinterpret_cast<float*>(smem);
@@ -229,6 +330,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
   uint64_t* done = empty + kK1Stages;                   // [2] scan finished in staging buf
   uint64_t* sfree = done + 2;                           // [2] staging buf flushed
   uint32_t* norm_acc = reinterpret_cast<uint32_t*>(sfree + 2);  // [2]
+  float* sums_s = reinterpret_cast<float*>(tail + 256);         // SUMS: [2][kK1SumBuf] partials | [232] final
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -260,9 +362,9 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
   if (warp < kRowWarps) {
     // ------------------------------------------------------------------ row warps
     if (warp == kRowWarps - 1)
-      k1_row_warp<OutT, kSY - 4 * (kRowWarps - 1)>(p, slabs, stg0, full, empty, done, sfree, norm_acc, warp, lane);
+      k1_row_warp<OutT, kSY - 4 * (kRowWarps - 1), SUMS>(p, slabs, stg0, full, empty, done, sfree, norm_acc, sums_s, warp, lane);
     else
-      k1_row_warp<OutT, 4>(p, slabs, stg0, full, empty, done, sfree, norm_acc, warp, lane);
+      k1_row_warp<OutT, 4, SUMS>(p, slabs, stg0, full, empty, done, sfree, norm_acc, sums_s, warp, lane);
   } else if (warp < kRowWarps + kColWarps) {
     // ------------------------------------------------------------------ column warps
     const int c = warp - kRowWarps;
@@ -270,12 +372,9 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
     for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++t) {
       const int buf = t & 1;
       OutT* stg;
-      if (K1Cfg<OutT>::kDirect) {
-        stg = reinterpret_cast<OutT*>(p.feats) + b * static_cast<int64_t>(p.stride);
-      } else {
-        stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
-        mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
-      }
+      if (K1Cfg<OutT>::kDirect) stg = reinterpret_cast<OutT*>(p.feats) + b * static_cast<int64_t>(p.stride);
+      else stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
+      if (kSync) mbar_wait(&sfree[buf], ((t >> 1) & 1) ^ 1);
       for (int i = 0; i < kSX; ++i, ++it) {
         if ((it % kColWarps) != static_cast<uint32_t>(c)) continue;   // ownership follows the ring slot
         const int stage = it % kK1Stages;
@@ -310,8 +409,8 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
         if (lane == 0 && tot) atomicAdd(&norm_acc[buf], tot);
         sumsq = 0;
       }
-      if (!K1Cfg<OutT>::kDirect) {
-        fence_proxy_async_smem();
+      if (kSync) {
+        if (!K1Cfg<OutT>::kDirect) fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&done[buf]);
       }
@@ -334,18 +433,24 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_project_max(const K1Params p
         }
       }
     }
-  } else if (!K1Cfg<OutT>::kDirect) {
-    // ------------------------------------------------------------------ flusher (u8 rows)
+  } else if (kSync) {
+    // ------------------------------------------------------------------ flusher (u8 rows, axis sums)
     for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++t) {
       const int buf = t & 1;
       OutT* stg = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(stg0) + buf * kStgBytes);
       mbar_wait(&done[buf], (t >> 1) & 1);
-      if (sizeof(OutT) == 1) {
+      if (sizeof(OutT) == 1 && lane == 0) {
+        bulk_s2g(reinterpret_cast<uint8_t*>(p.feats) + b * p.stride, stg, p.stride);
+        bulk_commit();
+        if (p.norms) p.norms[b] = static_cast<int32_t>(norm_acc[buf]);
+        norm_acc[buf] = 0;
+      }
+      if (SUMS) k1_rank_targets(p, sums_s + buf * kK1SumBuf, sums_s + 2 * kK1SumBuf, b, lane);   // under the bulk store
+      if (K1Cfg<OutT>::kDirect) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sfree[buf]);
+      } else if (sizeof(OutT) == 1) {
         if (lane == 0) {
-          bulk_s2g(reinterpret_cast<uint8_t*>(p.feats) + b * p.stride, stg, p.stride);
-          bulk_commit();
-          if (p.norms) p.norms[b] = static_cast<int32_t>(norm_acc[buf]);
-          norm_acc[buf] = 0;
           bulk_wait_read<0>();
           mbar_arrive(&sfree[buf]);
           if (p.tile_done) {

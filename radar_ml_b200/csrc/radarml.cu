@@ -341,6 +341,8 @@ cudaError_t opt_in_smem(K kernel) {
 int set_kernel_attributes(rml_ctx* c) {
   RML_CUDA(c, opt_in_smem(k1_project_max<uint8_t>));
   RML_CUDA(c, opt_in_smem(k1_project_max<float>));
+  RML_CUDA(c, opt_in_smem(k1_project_max<uint8_t, true>));
+  RML_CUDA(c, opt_in_smem(k1_project_max<float, true>));
   RML_CUDA(c, opt_in_smem(k1_project_max_u8in<uint8_t>));
   RML_CUDA(c, opt_in_smem(k1_project_max_u8in<float>));
   RML_CUDA(c, opt_in_smem(k2_rbf_i8<2>)); RML_CUDA(c, opt_in_smem(k2_rbf_i8<3>)); RML_CUDA(c, opt_in_smem(k2_rbf_i8<4>));
@@ -361,10 +363,16 @@ int set_kernel_attributes(rml_ctx* c) {
 }
 
 // cubes: float32 voxels (predict.py:91) or, with cube_u8 != 0, the sensor's integers as uint8
+// derive != null (fast path only): DerivedTarget's axis sums and top-T indices from the same pass
+struct DeriveOut {
+  int T;
+  int32_t* ijk;
+  float* sums;
+};
 int project_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32_t* ijk,
                  uint32_t mask, int dtype, void* feats, int32_t* norms, cudaStream_t st,
                  int grid_limit = 0, unsigned int* tile_done = nullptr, const Affine* aff_in = nullptr,
-                 int cube_u8 = 0, int64_t cube_stride = -1) {
+                 int cube_u8 = 0, int64_t cube_stride = -1, const DeriveOut* derive = nullptr) {
   const Affine aff = aff_in ? *aff_in : Affine{c->aff_offset, c->aff_scale, c->aff_enabled, c->aff_off_dev, c->aff_scl_dev};
   if (B < 0 || !cubes || !feats) return fail(c, RML_E_INVALID, "rml_project: null buffer or B<0");
   if (aff.off_tab && aff.enabled && dtype == RML_F32 && c->aff_F != feature_len(c, mask))
@@ -376,6 +384,7 @@ int project_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32
   if (mode == RML_MODE_SLICE && !ijk) return fail(c, RML_E_INVALID, "SLICE mode needs ijk");
   if (dtype != RML_F32 && dtype != RML_U8) return fail(c, RML_E_INVALID, "bad dtype %d", dtype);
   const bool fast = mode == RML_MODE_MAX && c->sx == kSX && c->sy == kSY && c->sz == kSZ && cube_stride < 0;
+  if (derive && (!fast || cube_u8)) return fail(c, RML_E_UNSUPPORTED, "project_impl: fused derive needs the default arena and float32 cubes");
   // bulk copies / float4 loads need 16-byte granules; uint8 cubes outside the streaming kernel
   // are read as uchar4 at most
   const uintptr_t cube_align = (cube_u8 && !fast) ? 3 : 15;
@@ -410,9 +419,13 @@ int project_impl(rml_ctx* c, const void* cubes, int64_t B, int mode, const int32
     p.aff_off = aff.off_tab; p.aff_scl = aff.scl_tab;
     p.tile_done = dtype == RML_U8 ? tile_done : nullptr;
     p.split = c->k1_split;
+    p.dt_ijk = derive ? derive->ijk : nullptr; p.dt_sums = derive ? derive->sums : nullptr; p.dt_T = derive ? derive->T : 0;
     const int sms = grid_limit > 0 ? grid_limit : c->num_sms;
     const int grid = static_cast<int>(B < sms ? B : sms);
-    if (dtype == RML_U8) {
+    if (derive) {
+      if (dtype == RML_U8) k1_project_max<uint8_t, true><<<grid, kK1Threads, k1_smem_bytes<uint8_t, true>(), st>>>(p);
+      else k1_project_max<float, true><<<grid, kK1Threads, k1_smem_bytes<float, true>(), st>>>(p);
+    } else if (dtype == RML_U8) {
       const int smem = k1_smem_bytes<uint8_t>();
       k1_project_max<uint8_t><<<grid, kK1Threads, smem, st>>>(p);
     } else {
@@ -1497,6 +1510,25 @@ int rml_derive_targets(rml_ctx* c, const float* cubes, int64_t B, int num_target
   RML_CUDA(c, cudaGetLastError());
   ++c->launches;
   return RML_OK;
+}
+
+int rml_project_derive(rml_ctx* c, const float* cubes, int64_t B, uint32_t mask, int dtype, void* feats,
+                       int32_t* norms, int num_targets, int32_t* ijk, float* sums, rml_stream stream) {
+  if (!c) return RML_E_INVALID;
+  if (!ijk || num_targets < 1 || num_targets > kK1MaxTargets || num_targets > c->sx || num_targets > c->sy ||
+      num_targets > c->sz)
+    return fail(c, RML_E_INVALID, "rml_project_derive: bad arguments");
+  DeviceGuard g(c->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->sx == kSX && c->sy == kSY && c->sz == kSZ) {
+    // ONE pass over the cube: the projection kernel's row warps also accumulate the three axis sums
+    const DeriveOut dv{num_targets, ijk, sums};
+    return project_impl(c, cubes, B, RML_MODE_MAX, nullptr, mask, dtype, feats, norms, st, 0, nullptr, nullptr, 0, -1, &dv);
+  }
+  // other arenas: the generic projection kernel, then the stand-alone axis-sum kernel (two passes)
+  int rc = project_impl(c, cubes, B, RML_MODE_MAX, nullptr, mask, dtype, feats, norms, st);
+  if (rc) return rc;
+  return rml_derive_targets(c, cubes, B, num_targets, ijk, sums, stream);
 }
 
 int rml_set_zoom(rml_ctx* c, int proj, int in_h, int in_w, int out_h, int out_w,

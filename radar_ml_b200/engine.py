@@ -211,6 +211,24 @@ class Engine:
                                                         _ptr(sums), self._stream()))
         return (ijk, sums) if want_sums else ijk
 
+    def project_derive(self, cubes, num_targets=1, mask=MASK_ALL, dtype=F32, want_sums=False):
+        """``project(mode='max')`` and ``derive_targets`` in ONE pass over the cubes (default arena;
+        other arenas run the two kernels back to back).  Returns (features[, norms], ijk[, sums])."""
+        if self._check_cubes(cubes):
+            raise ValueError("project_derive takes float32 cubes")
+        m = mask_bits(mask)
+        B = cubes.shape[0]
+        out = torch.empty((B, self.feature_stride(m, dtype)), device=self.device,
+                          dtype=torch.uint8 if dtype == U8 else torch.float32)
+        norms = torch.empty((B,), device=self.device, dtype=torch.int32) if dtype == U8 else None
+        ijk = torch.empty((B, num_targets, 3), device=self.device, dtype=torch.int32)
+        sums = torch.empty((B, sum(self.dims)), device=self.device, dtype=torch.float32) if want_sums else None
+        if B:
+            check(self.ctx, self.lib.rml_project_derive(self.ctx, _ptr(cubes), B, m, dtype, _ptr(out), _ptr(norms),
+                                                        num_targets, _ptr(ijk), _ptr(sums), self._stream()))
+        res = (out, norms) if dtype == U8 else (out,)
+        return res + ((ijk, sums) if want_sums else (ijk,))
+
     def set_zoom(self, proj, a_rows, a_cols):
         """Separable ndimage.zoom operator of projection ``proj`` (0 xz, 1 yz, 2 xy):
         a_rows [out_h, in_h], a_cols [out_w, in_w] float64 host arrays."""

@@ -280,6 +280,39 @@ def test_derive_targets_nan_sums_do_not_corrupt(eng, small_problem):
     assert (ijk >= 0).all() and (ijk[..., 0] < 22).all() and (ijk[..., 1] < 31).all() and (ijk[..., 2] < 176).all()
 
 
+def test_project_derive_shares_one_pass(eng, small_problem):
+    """DerivedTarget's axis sums (common.py:45-80) computed inside K1's single pass
+    over the cube.  Same features / norms as rml_project, same indices and sums as rml_derive_targets
+    and as the reference formula (integer-valued cubes: float32 sums are exact in any order)."""
+    import torch
+    from radar_ml_b200._lib import F32, U8
+    cubes = small_problem["cubes"][:301]                       # ragged against the persistent grid
+    d = torch.from_numpy(cubes).cuda()
+    ijk_ref, sums_ref = eng.derive_targets(d, num_targets=3, want_sums=True)
+    f32_ref = eng.project(d, dtype=F32)
+    u8_ref, norms_ref = eng.project(d, dtype=U8)
+    f32, ijk_a, sums_a = eng.project_derive(d, num_targets=3, dtype=F32, want_sums=True)
+    u8, norms, ijk_b = eng.project_derive(d, num_targets=3, dtype=U8)
+    eng.check_status()
+    assert torch.equal(f32, f32_ref) and torch.equal(u8, u8_ref) and torch.equal(norms, norms_ref)
+    assert torch.equal(sums_a, sums_ref)
+    assert torch.equal(ijk_a, ijk_ref) and torch.equal(ijk_b, ijk_ref)
+    # the reference formula itself: sums over the other two axes, argsort, last = strongest
+    c64 = cubes.astype(np.float64)
+    want = np.concatenate([c64.sum(axis=(2, 3)), c64.sum(axis=(1, 3)), c64.sum(axis=(1, 2))], axis=1)
+    assert np.array_equal(sums_a.cpu().numpy().astype(np.float64), want)
+    assert np.array_equal(sums_ref.cpu().numpy().astype(np.float64), want)
+    # NaN sums are reported, never turned into out-of-range indices
+    bad = cubes[:4].copy()
+    bad[2] = np.nan
+    _, ijk_n = eng.project_derive(torch.from_numpy(bad).cuda(), num_targets=2, dtype=F32)
+    from radar_ml_b200._lib import RadarMLError
+    with pytest.raises(RadarMLError):
+        eng.check_status()
+    ijk_n = ijk_n.cpu().numpy()
+    assert (ijk_n >= 0).all() and (ijk_n[..., 0] < 22).all() and (ijk_n[..., 1] < 31).all() and (ijk_n[..., 2] < 176).all()
+
+
 # --------------------------------------------------------------------------- label exchange
 def test_allgather_labels_single_rank_and_in_place(eng, small_problem):
     """world == 1: rml_allgather_labels degenerates to a copy; rml_predict writes its labels
