@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(256) k0_derive_targets(const DeriveParams p) {
           const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
           if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
+        __syncwarp();
         if (lane == 0) {
           if (bi >= n) {
             // no candidate compared greater than -FLT_MAX (NaN or -inf sums): take the lowest

@@ -302,6 +302,7 @@ __device__ __forceinline__ void k1_rank_targets(const K1Params& p, const float* 
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
       }
+      __syncwarp();
       if (lane == 0) {
         if (bi >= n) {     // NaN / -inf sums: lowest unused index, reported (status[3] -> RML_E_INVALID)
           bi = 0;

@@ -69,7 +69,7 @@ struct TowerParams {
   const float* b2;               // FUSE2: [3][C2]
   float alpha;                   // LeakyReLU slope (ACT == 2)
   int dbg;                       // experiments only (RML_T6_DBG): 64 = strided-column horizontal pass, 32 = gather after
-                                 // the layer-1 commit (same results);
+                                 // the layer-1 commit, 512 = barrier form of the mbarrier waits (same results);
                                  // 1 no layer-2 MMAs, 2 no resize, 4 no layer-1
                                  // epilogue, 8 no im2col, 16 no layer-1 MMAs — results are wrong with any bit set
   __nv_bfloat16* out;            // FUSE2: [B][3][H2][H2][C2]; else [B*3][H1][H1][C1]
@@ -315,6 +315,10 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // RML_T6_DBG=512: the long mbarrier waits in their "one warp polls, the others park on a bar.sync" form.
+  // Same protocol, 2 % slower; it is the form compute-sanitizer's racecheck can follow (it does not model an
+  // mbarrier acquire as a synchronisation edge), so the race-freedom of the hand-over is checked in this mode.
+  const bool bar_form = (p.dbg & 512) != 0;
 
   // image rows of block k: what T round k needs beyond block k-1 (rounds overlap by the 3x3 halo)
   auto blk_lo = [](int k) { return k == 0 ? 0 : (FUSE2 ? 4 * kT6TH * k + 3 : 16 * k + 1); };
@@ -349,7 +353,12 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
         if (iuse > 0) {
           // the T role is done with this block of the image that was here before (two image buffers:
           // normally long ago)
-          mbar_wait_relaxed(&empty[ibuf * NB + k], (iuse - 1) & 1);
+          if (bar_form) {
+            if (rt < 32) mbar_wait_relaxed(&empty[ibuf * NB + k], (iuse - 1) & 1);
+            bar_group(6, kT6RThreads);
+          } else {
+            mbar_wait_relaxed(&empty[ibuf * NB + k], (iuse - 1) & 1);
+          }
         }
         const int lo = blk_lo(k), hi = blk_hi(k);
         if (p.images) {
@@ -418,6 +427,7 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
       // work, the 44 UMMAs of a round — one thread, ~2.5 k cycles — made group 0 the straggler at every
       // barrier: half of the tile role's time was barrier wait.)
       const bool mma_warp = warp == kT6TThreads / 32 - 1;
+      const int gthreads = grp == 3 ? 96 : 128;                    // group barrier without the issuer
       const int pidx = grp * 128 + m;                               // pixel of this thread inside a round
       const int prow = pidx / H1, x1 = pidx - prow * H1;
       const bool store = pidx < kPixPerStrip;
@@ -435,7 +445,12 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
         const uint32_t ibuf = im % NIMG, iuse = im / NIMG;
         // every warp acquires the barrier itself: it has normally completed long ago (the R role runs
         // ahead), and a group barrier behind one polling warp costs a round trip per round
-        mbar_wait_relaxed(&full[ibuf * NB + s], iuse & 1);
+        if (bar_form) {
+          if (q == 0) mbar_wait_relaxed(&full[ibuf * NB + s], iuse & 1);
+          bar_group(1 + grp, gthreads);
+        } else {
+          mbar_wait_relaxed(&full[ibuf * NB + s], iuse & 1);
+        }
         if (!warp_dead && !(p.dbg & 8)) {
           const int y1 = 2 * kT6TH * s + prow;
           const bool live = store && y1 < H1;                       // y1 == H1 is layer 2's zero pad row
@@ -546,7 +561,12 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
         if (!early && r + 1 < n_rounds) im2col(r + 1);
         if (r >= 1) {
           // the strip planes are still being read by the layer-2 UMMAs of round r-1
-          mbar_wait_relaxed(mbar2, (r - 1) & 1);
+          if (bar_form) {
+            if (q == 0) mbar_wait_relaxed(mbar2, (r - 1) & 1);
+            bar_group(1 + grp, gthreads);
+          } else {
+            mbar_wait_relaxed(mbar2, (r - 1) & 1);
+          }
         }
         if (r < n_rounds) {
           if (store && !warp_dead && !(p.dbg & 4)) {

@@ -46,6 +46,13 @@ Ph, lh, _ = eng.predict_host(test[:64])
 assert np.array_equal(lh, lab_o[:64])
 Pt, lt, _ = eng.predict_targets_host(test[0], ijk[160:164])
 Pg, lg, _ = eng.score_features_host(X[160:200])
+# DerivedTarget axis sums inside the projection pass (both output types) against the stand-alone kernel
+from radar_ml_b200._lib import F32 as _F32, U8 as _U8  # noqa: E402
+ijk_ref = eng.derive_targets(d, num_targets=3)
+f_a, ijk_a = eng.project_derive(d, num_targets=3, dtype=_F32)
+u_b, n_b, ijk_b = eng.project_derive(d, num_targets=3, dtype=_U8)
+eng.check_status()
+assert torch.equal(ijk_a, ijk_ref) and torch.equal(ijk_b, ijk_ref) and torch.equal(f_a, eng.project(d, dtype=_F32))
 # real-valued cubes -> float32 features -> multi-digit scorer
 eng.set_precision(True)
 real = (test[:64] * 0.73).astype(np.float32)
