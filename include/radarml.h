@@ -184,6 +184,25 @@ int rml_predict_host(rml_ctx* ctx, const float* cubes_host, int64_t B, int mode,
                      const int32_t* ijk_host, uint32_t mask, double min_proba, float* proba_host,
                      int32_t* label_host, uint8_t* known_host);
 
+/* rml_predict_host and integer-valued float32 cubes (predict.py:90-91 widens the sensor's integers
+ * 0..255 to float32): for a model on the integer path each chunk is converted back to bytes on the
+ * host (a pool of threads, every value checked to be exactly an integer in [0,255]) and a quarter
+ * of the bytes crosses PCIe; the device runs the uint8-cube kernels, whose results are identical bit
+ * for bit.  A chunk holding any other value is copied as float32 as before.  OFF by default (env
+ * RML_HOST_NARROW=1 enables): it pays only where the host converts faster than the bus moves float32
+ * bytes — on the B200 box (16 vCPUs, PCIe 5 x16) the conversion runs at 65-90 GB/s of float32 input
+ * against 53 GB/s over the bus, +3 % end to end (bench.py e2e.host_narrowing) — and it switches
+ * itself off when the conversion falls below min_gbs (default 60).  threads = 0: one per CPU of the
+ * process's affinity mask.  Call before rml_reserve(RML_RESERVE_HOST). */
+int rml_set_host_narrowing(rml_ctx* ctx, int enabled, int threads, double min_gbs);
+/* the conversion itself (host only, no GPU needed): dst_host[i] = (uint8_t)src_host[i]; RML_OK when every
+ * value is exactly an integer in [0,255], RML_E_NONINTEGRAL otherwise.  dst_host 32-byte aligned. */
+int rml_host_narrow_f32_to_u8(const float* src_host, uint8_t* dst_host, int64_t n, int threads);
+/* what the last rml_predict_host moved: bytes copied host->device, scans that crossed as bytes,
+ * float32 input rate of the last conversion (GB/s), pool threads, 1 while narrowing is active */
+int rml_last_host_transfer(const rml_ctx* ctx, int64_t* h2d_bytes, int64_t* narrowed_scans,
+                           double* convert_gbs, int* threads, int* active);
+
 /* Buffers the library owns are created here, never inside a hot entry point (SURVEY.md §8b
  * ownership row): call after the model is loaded, again after loading another model.
  *   RML_RESERVE_SCORE    digit-plane scratch so rml_score accepts float32 rows of up to max_batch

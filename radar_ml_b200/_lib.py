@@ -14,6 +14,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libradarml.so")
 SRC = os.path.join(_HERE, "csrc", "radarml.cu")
+HOST_SRC = os.path.join(_HERE, "csrc", "host_narrow.cpp")     # host-only code (thread pool, AVX2)
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "radarml.h")
 
 OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMODEL, E_NONINTEGRAL, E_RANGE = 0, -1, -2, -3, -4, -5, -6
@@ -40,13 +41,13 @@ class OutOfRangeInput(RadarMLError):
 def nvcc_command(out=LIB_PATH):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     return [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-            "-Xcompiler", "-fPIC", "-shared", "-o", out, SRC, "-ldl"]
+            "-Xcompiler", "-fPIC", "-shared", "-o", out, SRC, HOST_SRC, "-ldl", "-lpthread"]
 
 
 def build(force=False, verbose=False):
     """Compile libradarml.so for sm_100a if it is missing or older than its sources."""
     srcs = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))
-            if f.endswith((".cu", ".cuh", ".h"))] + [HEADER]
+            if f.endswith((".cu", ".cuh", ".h", ".cpp"))] + [HEADER]
     if not force and os.path.exists(LIB_PATH):
         if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs):
             return LIB_PATH
@@ -75,6 +76,10 @@ SIGNATURES = {
     "rml_load_affine": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "rml_set_precision": (C.c_int, [_vp, C.c_int]),
     "rml_reserve": (C.c_int, [_vp, _i64, C.c_int]),
+    "rml_set_host_narrowing": (C.c_int, [_vp, C.c_int, C.c_int, _f64]),
+    "rml_host_narrow_f32_to_u8": (C.c_int, [_vp, _vp, _i64, C.c_int]),
+    "rml_last_host_transfer": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_f64),
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rml_score_host": (C.c_int, [_vp, _vp, _i64, _f64, _vp, _vp, _vp]),
     "rml_predict_targets_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _u32, _f64, _vp, _vp, _vp]),
     "rml_comm_unique_id": (C.c_int, [_vp, _vp]),

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <initializer_list>
 #include <string>
 #include <vector>
@@ -24,6 +25,7 @@
 #include "k3_net.cuh"
 #include "k6_tower.cuh"
 #include "k0_extras.cuh"
+#include "host_narrow.h"
 
 using namespace rml;
 
@@ -72,6 +74,14 @@ struct HostPipe {
   uint8_t* known[kHostBufs] = {nullptr};
   cudaStream_t stream[kHostBufs] = {nullptr};
   size_t work_bytes = 0;
+  // host-side narrowing of integral float32 cubes to bytes before the H2D copy (host_narrow.h)
+  uint8_t* narrow_pin[kHostBufs] = {nullptr};      // pinned staging, chunk x cube elements each
+  cudaEvent_t narrow_ev[kHostBufs] = {nullptr};    // the H2D copy out of a staging buffer has finished
+  rml_host::NarrowPool* pool = nullptr;
+  int narrow_slow = 0;             // consecutive chunks whose conversion was slower than the float32 copy would be
+  bool narrow_off = false;         // switched off by that measurement (until the next rml_reserve)
+  double narrow_gbs = 0;           // float32 input rate of the last conversion
+  int64_t last_h2d_bytes = 0, last_narrowed = 0;   // of the last rml_predict_host call
 };
 
 // scratch of the small host-buffer calls (rml_score_host / rml_predict_targets_host): one scan's
@@ -155,6 +165,10 @@ struct rml_ctx {
   std::vector<double> aff_shift;  // offset[f] / scale[f]: makes standardised features non-negative (digit path)
   int k1_split = 1, k5_kpg = 0;   // tuning experiments (RML_K1_SPLIT, RML_K5_KPG), read once at create
   int force_f32 = 0;              // rml_set_precision: 1 = float32 features even for an integral model
+  int host_narrow = 0;            // rml_predict_host: integral float32 cubes cross the bus as bytes (rml_set_host_narrowing;
+                                  // off by default: on the B200 box the host converts at 65-90 GB/s, what PCIe moves anyway)
+  int host_narrow_threads = 0;    // conversion threads (0 = one per CPU of the process's affinity mask)
+  double host_narrow_min_gbs = 60.0;
   void* nccl_comm = nullptr;
   int nccl_rank = 0, nccl_world = 1;
   SmallPipe small;
@@ -671,7 +685,10 @@ void free_pipe(HostPipe& hp) {
     cudaFree(hp.cubes[i]); cudaFree(hp.ijk[i]); cudaFree(hp.work[i]);
     cudaFree(hp.proba[i]); cudaFree(hp.label[i]); cudaFree(hp.known[i]);
     if (hp.stream[i]) cudaStreamDestroy(hp.stream[i]);
+    if (hp.narrow_pin[i]) cudaFreeHost(hp.narrow_pin[i]);
+    if (hp.narrow_ev[i]) cudaEventDestroy(hp.narrow_ev[i]);
   }
+  rml_host::narrow_pool_destroy(hp.pool);
   hp = HostPipe();
 }
 
@@ -738,6 +755,8 @@ int rml_create(int device, rml_ctx** out) {
   if (const char* e5 = getenv("RML_K1U8_CTAS")) { const int v = atoi(e5); if (v == 1 || v == 2) c->k1u8_ctas_per_sm = v; }
   if (const char* e2 = getenv("RML_FUSED")) c->fused_enabled = atoi(e2);
   if (const char* e3 = getenv("RML_FUSED_MIN_B")) c->fused_min_b = atoll(e3);
+  if (const char* e6 = getenv("RML_HOST_NARROW")) c->host_narrow = atoi(e6) != 0;
+  if (const char* e7 = getenv("RML_HOST_NARROW_THREADS")) c->host_narrow_threads = atoi(e7);
   *out = c;
   return RML_OK;
 }
@@ -1134,6 +1153,14 @@ int reserve_host_pipe(rml_ctx* c, int cube_u8) {
   }
   hp.chunk = chunk;
   hp.cube_bytes = cube_bytes;
+  if (!cube_u8 && c->host_narrow) {
+    // float32 cubes of the sensor's integers cross the bus as bytes (see host_narrow.h)
+    for (int i = 0; i < kHostBufs; ++i) {
+      RML_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&hp.narrow_pin[i]), chunk * (cube_bytes / 4), cudaHostAllocDefault));
+      RML_CUDA(c, cudaEventCreateWithFlags(&hp.narrow_ev[i], cudaEventDisableTiming));
+    }
+    hp.pool = rml_host::narrow_pool_create(c->host_narrow_threads);
+  }
   return RML_OK;
 }
 
@@ -1191,15 +1218,53 @@ int predict_host_impl(rml_ctx* c, const void* cubes_host, int cube_u8, int64_t B
   const char* src = static_cast<const char*>(cubes_host);
   int64_t done = 0;
   int slot = 0;
+  // integral float32 cubes go over the bus as bytes when the model is on the integer path: the
+  // conversion of chunk n+1 (host threads) overlaps the copy and the kernels of chunk n
+  const bool narrow = !cube_u8 && hp.pool && !hp.narrow_off && use_u8_path(c);
+  const size_t cube_elems = cube_bytes / (cube_u8 ? 1 : 4);
+  hp.last_h2d_bytes = 0;
+  hp.last_narrowed = 0;
   while (done < B) {
     const int64_t n = (B - done) < chunk ? (B - done) : chunk;
     cudaStream_t st = hp.stream[slot];
-    RML_CUDA(c, cudaMemcpyAsync(hp.cubes[slot], src + done * cube_bytes, n * cube_bytes,
-                                cudaMemcpyHostToDevice, st));
+    int as_u8 = cube_u8;
+    if (narrow && !hp.narrow_off && n >= 32) {      // a few scans are quicker to copy than to hand to the pool
+      const auto tw = std::chrono::steady_clock::now();
+      RML_CUDA(c, cudaEventSynchronize(hp.narrow_ev[slot]));     // the previous copy out of this staging buffer
+      const auto t0 = std::chrono::steady_clock::now();
+      const int bad = rml_host::narrow_f32_to_u8(hp.pool, reinterpret_cast<const float*>(src + done * cube_bytes),
+                                                 hp.narrow_pin[slot], static_cast<size_t>(n) * cube_elems);
+      const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      hp.narrow_gbs = static_cast<double>(n) * cube_bytes / sec * 1e-9;
+      static const bool trace = getenv("RML_HOST_NARROW_TRACE") != nullptr;
+      if (trace)
+        fprintf(stderr, "[narrow] chunk at %lld: waited %.3f ms for the staging buffer, converted %lld scans in %.3f ms (%.1f GB/s), %s\n",
+                static_cast<long long>(done), std::chrono::duration<double>(t0 - tw).count() * 1e3,
+                static_cast<long long>(n), sec * 1e3, hp.narrow_gbs, bad ? "NOT integral" : "integral");
+      // narrowing only pays while the host converts faster than the bus would move the float32 bytes
+      // (PCIe 5 x16: ~53 GB/s); a busy or narrow host switches it off until the next rml_reserve
+      if (n == chunk) {
+        hp.narrow_slow = hp.narrow_gbs < c->host_narrow_min_gbs ? hp.narrow_slow + 1 : 0;
+        if (hp.narrow_slow >= 3) hp.narrow_off = true;
+      }
+      if (!bad) {
+        RML_CUDA(c, cudaMemcpyAsync(hp.cubes[slot], hp.narrow_pin[slot], static_cast<size_t>(n) * cube_elems,
+                                    cudaMemcpyHostToDevice, st));
+        RML_CUDA(c, cudaEventRecord(hp.narrow_ev[slot], st));
+        as_u8 = 1;
+        hp.last_h2d_bytes += n * static_cast<int64_t>(cube_elems);
+        hp.last_narrowed += n;
+      }
+    }
+    if (as_u8 == cube_u8) {
+      RML_CUDA(c, cudaMemcpyAsync(hp.cubes[slot], src + done * cube_bytes, n * cube_bytes,
+                                  cudaMemcpyHostToDevice, st));
+      hp.last_h2d_bytes += n * static_cast<int64_t>(cube_bytes);
+    }
     if (mode == RML_MODE_SLICE)
       RML_CUDA(c, cudaMemcpyAsync(hp.ijk[slot], ijk_host + done * 3, n * 12, cudaMemcpyHostToDevice, st));
     int rc = predict_impl(c, hp.cubes[slot], n, mode, hp.ijk[slot], mask, min_proba, hp.work[slot],
-                          hp.proba[slot], hp.label[slot], hp.known[slot], st, cube_u8);
+                          hp.proba[slot], hp.label[slot], hp.known[slot], st, as_u8);
     if (rc) return rc;
     RML_CUDA(c, cudaMemcpyAsync(proba_host + done * C, hp.proba[slot], n * C * 4, cudaMemcpyDeviceToHost, st));
     RML_CUDA(c, cudaMemcpyAsync(label_host + done, hp.label[slot], n * 4, cudaMemcpyDeviceToHost, st));
@@ -1305,6 +1370,38 @@ int rml_predict_host(rml_ctx* c, const float* cubes_host, int64_t B, int mode,
                      int32_t* label_host, uint8_t* known_host) {
   return predict_host_impl(c, cubes_host, 0, B, mode, ijk_host, mask, min_proba, proba_host,
                            label_host, known_host);
+}
+
+int rml_set_host_narrowing(rml_ctx* c, int enabled, int threads, double min_gbs) {
+  if (!c) return RML_E_INVALID;
+  c->host_narrow = enabled ? 1 : 0;
+  c->host_narrow_threads = threads > 0 ? threads : 0;
+  if (min_gbs > 0) c->host_narrow_min_gbs = min_gbs;
+  // takes effect at the next rml_reserve(RML_RESERVE_HOST): drop the current staging
+  DeviceGuard g(c->device);
+  cudaDeviceSynchronize();
+  free_pipe(c->pipe);
+  return RML_OK;
+}
+
+int rml_host_narrow_f32_to_u8(const float* src_host, uint8_t* dst_host, int64_t n, int threads) {
+  if (!src_host || !dst_host || n < 0 || (reinterpret_cast<uintptr_t>(dst_host) & 31)) return RML_E_INVALID;
+  rml_host::NarrowPool* pool = threads == 1 ? nullptr : rml_host::narrow_pool_create(threads);
+  const int bad = rml_host::narrow_f32_to_u8(pool, src_host, dst_host, static_cast<size_t>(n));
+  rml_host::narrow_pool_destroy(pool);
+  return bad ? RML_E_NONINTEGRAL : RML_OK;
+}
+
+int rml_last_host_transfer(const rml_ctx* c, int64_t* h2d_bytes, int64_t* narrowed_scans, double* convert_gbs,
+                           int* threads, int* active) {
+  if (!c) return RML_E_INVALID;
+  const HostPipe& hp = c->pipe;
+  if (h2d_bytes) *h2d_bytes = hp.last_h2d_bytes;
+  if (narrowed_scans) *narrowed_scans = hp.last_narrowed;
+  if (convert_gbs) *convert_gbs = hp.narrow_gbs;
+  if (threads) *threads = rml_host::narrow_pool_threads(hp.pool);
+  if (active) *active = hp.pool && !hp.narrow_off;
+  return RML_OK;
 }
 
 int rml_predict_host_u8(rml_ctx* c, const uint8_t* cubes_host, int64_t B, int mode,

@@ -105,6 +105,23 @@ class Engine:
             check(self.ctx, self.lib.rml_reserve(self.ctx, int(rows), flag))
             self._reserved[flag] = rows
 
+    def set_host_narrowing(self, enabled=True, threads=0, min_gbs=0.0):
+        """``predict_host`` on float32 cubes of the sensor's integers: convert each chunk to bytes on
+        the host (thread pool, exactness checked) so a quarter of the bytes crosses PCIe.  Off by
+        default (it needs a host that converts faster than the bus moves float32 bytes); switches
+        itself off when the host converts slower than ``min_gbs`` (60 GB/s)."""
+        check(self.ctx, self.lib.rml_set_host_narrowing(self.ctx, int(bool(enabled)), int(threads), float(min_gbs)))
+        self._reserved.pop(RESERVE_HOST, None)
+        self._reserved.pop(RESERVE_HOST_U8, None)
+
+    def last_host_transfer(self):
+        """What the last ``predict_host`` moved: bus bytes, scans narrowed to bytes, conversion rate."""
+        b, n, g = C.c_int64(), C.c_int64(), C.c_double()
+        t, a = C.c_int(), C.c_int()
+        check(self.ctx, self.lib.rml_last_host_transfer(self.ctx, C.byref(b), C.byref(n), C.byref(g), C.byref(t), C.byref(a)))
+        return {"h2d_bytes": b.value, "narrowed_scans": n.value, "convert_gbs": g.value, "threads": t.value,
+                "active": bool(a.value)}
+
     def feature_len(self, mask=MASK_ALL):
         return self.lib.rml_feature_len(self.ctx, mask_bits(mask))
 

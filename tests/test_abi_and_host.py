@@ -46,6 +46,30 @@ def test_no_gpu_means_loud_failure_not_fallback(lib):
         Engine(0)
 
 
+def test_host_narrowing_conversion_is_exact_and_strict(lib):
+    """rml_predict_host narrows float32 cubes of the sensor's integers to bytes before the H2D copy
+    (host threads, no GPU involved): exact for integers in [0,255], refused for anything else."""
+    from radar_ml_b200._lib import E_NONINTEGRAL
+    rng = np.random.default_rng(3)
+    n = 3 * 120032 + 17                                   # ragged against the 32-element blocks
+    src = rng.integers(0, 256, n).astype(np.float32)
+    src[5] = -0.0
+    raw = np.empty(n + 64, np.uint8)
+    off = (-raw.ctypes.data) % 32
+    dst = raw[off:off + n]
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for threads in (1, 3, 0):
+        dst[:] = 7
+        assert lib.rml_host_narrow_f32_to_u8(p(src), p(dst), n, threads) == 0
+        assert np.array_equal(dst, src.astype(np.uint8))
+    for pos, v in ((0, 0.5), (n - 1, 256.0), (70001, -1.0), (n // 2, np.nan), (n - 40, np.inf), (33, 254.99998)):
+        bad = src.copy()
+        bad[pos] = v
+        for threads in (1, 4):
+            assert lib.rml_host_narrow_f32_to_u8(p(bad), p(dst), n, threads) == E_NONINTEGRAL, (pos, v, threads)
+    assert lib.rml_host_narrow_f32_to_u8(p(src), p(raw[off + 1:]), 64, 1) != 0      # misaligned destination
+
+
 def test_package_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "radar_ml_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -313,6 +313,41 @@ def test_project_derive_shares_one_pass(eng, small_problem):
     assert (ijk_n >= 0).all() and (ijk_n[..., 0] < 22).all() and (ijk_n[..., 1] < 31).all() and (ijk_n[..., 2] < 176).all()
 
 
+def test_host_narrowing_same_results_quarter_of_the_bytes(eng, small_problem):
+    """rml_predict_host: float32 cubes of the sensor's integers cross the bus as bytes (converted and
+    checked on the host); results are those of the float32 transfer bit for bit, and a chunk with a
+    real value in it is copied as float32 and handled exactly as before."""
+    from radar_ml_b200.model import from_sklearn
+    eng.load_model(from_sklearn(small_problem["cal"]))
+    cubes = np.ascontiguousarray(np.concatenate([small_problem["cubes"][300:]] * 7)[:700])    # 2 chunks (512 + 188)
+    assert cubes.shape[0] == 700
+    eng.set_host_narrowing(True, threads=4, min_gbs=1e-3)          # never switch off in this test
+    P1, l1, k1 = eng.predict_host(cubes)
+    x = eng.last_host_transfer()
+    assert x["active"] and x["narrowed_scans"] == 700 and x["h2d_bytes"] == 700 * 22 * 31 * 176
+    eng.set_host_narrowing(False)
+    P0, l0, k0 = eng.predict_host(cubes)
+    x0 = eng.last_host_transfer()
+    assert x0["narrowed_scans"] == 0 and x0["h2d_bytes"] == 700 * 22 * 31 * 176 * 4
+    assert np.array_equal(P1, P0) and np.array_equal(l1, l0) and np.array_equal(k1, k0)
+    # SLICE mode through the narrowed path
+    ijk = small_problem["ijk"][300:][:64]
+    eng.set_host_narrowing(True, threads=4, min_gbs=1e-3)
+    Ps, ls, _ = eng.predict_host(cubes[:64], mode="slice", ijk=ijk)
+    eng.set_host_narrowing(False)
+    Pq, lq, _ = eng.predict_host(cubes[:64], mode="slice", ijk=ijk)
+    assert np.array_equal(Ps, Pq) and np.array_equal(ls, lq)
+    # one real-valued voxel in the second chunk: that chunk goes over as float32, the engine then
+    # re-scores the batch on the general-precision path, exactly as without narrowing
+    real = cubes.copy()
+    real[600, 3, 4, 5] += 0.25
+    eng.set_host_narrowing(True, threads=4, min_gbs=1e-3)
+    Pr, lr, _ = eng.predict_host(real)
+    eng.set_host_narrowing(False)
+    Pn, ln, _ = eng.predict_host(real)
+    assert np.array_equal(lr, ln) and np.array_equal(Pr, Pn)
+
+
 # --------------------------------------------------------------------------- label exchange
 def test_allgather_labels_single_rank_and_in_place(eng, small_problem):
     """world == 1: rml_allgather_labels degenerates to a copy; rml_predict writes its labels
