@@ -103,7 +103,7 @@ def device_cubes(n, seed, device, chunk=1024, integer=True):
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled through NVML every ~2 ms DURING the timed region
+    """SM clock + throttle reasons sampled through NVML every ~5 ms DURING the timed region
     (the recipe's nvidia-smi line needs >= 100 ms per sample; a timed region here is ~50 ms)."""
     BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
             0x4: "sw_power_cap"}
@@ -142,7 +142,8 @@ class ClockSampler:
             except Exception:
                 pass
             it += 1
-            time.sleep(0.001)
+            time.sleep(0.004)      # every NVML query takes the driver's lock: poll gently (a 1 ms poll cost the
+                                   # timed region up to 4 % on a box whose NVML calls took 2.5 ms each)
 
     def stop(self):
         self._stop.set()
