@@ -244,6 +244,10 @@ struct DgQuantParams {
   double scale;
   const double* shift;    // nullable [F]: added before scaling (standardised features -> non-negative)
 };
+// one warp per scan, eight scans per CTA; a lane takes 4 consecutive features per step (two float2 loads —
+// rows of 10 010 floats are only 8-byte aligned — and one 32-bit store per digit plane), so every access of
+// a warp is a contiguous 512 / 128-byte segment.  (The first version moved single bytes per lane and took
+// 1.01 ms per 32 768 scans, 20 % of the general-precision path; the pass moves 70 KB per scan.)
 __global__ void __launch_bounds__(256) k1_quantize_digits(const DgQuantParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t b = blockIdx.x * 8ll + warp;
@@ -251,20 +255,39 @@ __global__ void __launch_bounds__(256) k1_quantize_digits(const DgQuantParams p)
   const float* x = p.feats + b * p.F;
   const int64_t plane = p.B * static_cast<int64_t>(p.stride);
   uint8_t* o = p.planes + b * p.stride;
+  const double k = p.scale * 65536.0;
   unsigned long long sumsq = 0;
   uint32_t bad = 0;
-  for (int f = lane; f < p.stride; f += 32) {
-    uint32_t X = 0;
-    if (f < p.F) {
-      const double xs = p.shift ? static_cast<double>(x[f]) + p.shift[f] : static_cast<double>(x[f]);
-      const double v = rint(xs * p.scale * 65536.0);
-      bad |= !(v >= 0.0 && v < 16777216.0);
-      X = static_cast<uint32_t>(fmin(fmax(v, 0.0), 16777215.0));
+  const bool even_row = ((b * p.F) & 1) == 0;      // float2 loads need an 8-byte aligned pair
+  for (int f = 4 * lane; f < p.stride; f += 128) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (even_row && f + 3 < p.F) {
+      const float2 a = *reinterpret_cast<const float2*>(x + f);
+      const float2 c = *reinterpret_cast<const float2*>(x + f + 2);
+      v[0] = a.x; v[1] = a.y; v[2] = c.x; v[3] = c.y;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (f + q < p.F) v[q] = x[f + q];
     }
-    o[f] = static_cast<uint8_t>(X & 255u);
-    o[plane + f] = static_cast<uint8_t>((X >> 8) & 255u);
-    o[2 * plane + f] = static_cast<uint8_t>(X >> 16);
-    sumsq += static_cast<unsigned long long>(X) * X;
+    uint32_t d0 = 0, d1 = 0, d2 = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t X = 0;
+      if (f + q < p.F) {
+        const double xs = p.shift ? static_cast<double>(v[q]) + p.shift[f + q] : static_cast<double>(v[q]);
+        const double r = rint(xs * k);              // = rint(xs * scale * 65536): the power of two is exact
+        bad |= !(r >= 0.0 && r < 16777216.0);
+        X = static_cast<uint32_t>(fmin(fmax(r, 0.0), 16777215.0));
+      }
+      d0 |= (X & 255u) << (8 * q);
+      d1 |= ((X >> 8) & 255u) << (8 * q);
+      d2 |= (X >> 16) << (8 * q);
+      sumsq += static_cast<unsigned long long>(X) * X;
+    }
+    *reinterpret_cast<uint32_t*>(o + f) = d0;
+    *reinterpret_cast<uint32_t*>(o + plane + f) = d1;
+    *reinterpret_cast<uint32_t*>(o + 2 * plane + f) = d2;
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) sumsq += __shfl_xor_sync(0xffffffffu, sumsq, off);
