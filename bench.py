@@ -29,10 +29,11 @@ sys.path.insert(0, ROOT)
 
 CUBE_BYTES = 22 * 31 * 176 * 4            # 480 128 B, common.py:25-27
 ALGO_BYTES_PER_SCAN = CUBE_BYTES + 12 + 4  # + 3 fp32 probs + int32 label
-# dram__bytes_read.sum + dram__bytes_write.sum of k1_project_max<u8> per scan, from the ncu
-# --set full capture summarised in profiles/r1b_k1_project_max_u8_ncu.txt (7.86665 GB read +
-# 0.12745 GB written for 16 384 scans): 1.016 x the algorithmic bytes, i.e. no re-reads.
-K1_DRAM_TRAFFIC_PER_SCAN = (7.866650e9 + 127.451904e6) / 16384
+# dram__bytes_read.sum + dram__bytes_write.sum of k1_project_max<u8> per scan, from the round-2 ncu
+# --set full capture summarised in profiles/r2_k1_project_max_u8_ncu.txt (7.867382 GB read +
+# 0.122009 GB written for 16 384 scans; round 1: 7.86665 + 0.12745): 1.016 x the algorithmic bytes,
+# i.e. no re-reads.
+K1_DRAM_TRAFFIC_PER_SCAN = (7.867382e9 + 122.009088e6) / 16384
 METRIC = "radar_scans_per_sec_proj_classify"
 
 
@@ -789,7 +790,7 @@ def run_ours(args):
                                    "into the gather buffer" if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "kernel": "k1_project_max<u8>", "achieved": k1_gbs, "peak": peak,
                          "unit": "GB/s", "frac": k1_gbs / peak, "traffic": B * K1_DRAM_TRAFFIC_PER_SCAN,
-                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1b_k1_project_max_u8_ncu.txt)",
+                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r2_k1_project_max_u8_ncu.txt)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_scan": CUBE_BYTES, "k1_ms": k1_ms,
                          "k2_exposed_ms": k2_ms, "fused_pipeline": bool(fused),
