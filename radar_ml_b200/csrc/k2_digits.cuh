@@ -132,6 +132,7 @@ k2_rbf_digits(const __grid_constant__ DgMaps maps, const K2DgParams p) {
     }
   } else if (warp == 1) {
     const uint32_t idesc = umma_idesc(kCS32, kFmtU8, kFmtU8, kK2BlockM, kDgTileN);
+    const uint32_t idesc2 = umma_idesc(kCS32, kFmtU8, kFmtU8, kK2BlockM, 2 * kDgTileN);
     uint32_t kit = 0, ait = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int ch = 0; ch < p.n_chunks; ++ch, ++ait) {
@@ -144,19 +145,29 @@ k2_rbf_digits(const __grid_constant__ DgMaps maps, const K2DgParams p) {
           if (elect_one()) {
             const uint32_t a_addr = smem_u32(smem + s * kDgStageBytes);
             const uint32_t b_addr = a_addr + 3 * kDgABytes;
+            // Nine digit products per K step, six instructions: the support-vector digit tiles 0 and 1 are
+            // contiguous in the stage (12 groups of 8 rows each), and so are the accumulators of powers p
+            // and p+1, so A_a x [B_0 | B_1] is ONE UMMA of N = 192 into [acc_a | acc_a+1] — every A tile
+            // is read from shared memory twice instead of three times.  Order: the three N = 96 products
+            // with B_2 first (they initialise acc_2..4), then a = 0 (initialises acc_0 | acc_1), then
+            // a = 1, 2, which only ever accumulate.
+            const bool init = kb == 0;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
+              const uint64_t da = umma_desc_k_sw128(a_addr + a * kDgABytes);
+              const uint64_t db = umma_desc_k_sw128(b_addr + 2 * kDgBBytes);
 #pragma unroll
-              for (int b = 0; b < 3; ++b) {
-                const uint64_t da = umma_desc_k_sw128(a_addr + a * kDgABytes);
-                const uint64_t db = umma_desc_k_sw128(b_addr + b * kDgBBytes);
-                const uint32_t d_tmem = tmem_base + (a + b) * kDgTileN;
-                const bool first_pair = (a == 0) || (b == 2);   // first (a,b) of its power a+b
+              for (int ks = 0; ks < kK2BlockKBytes / 32; ++ks)
+                umma_i8(tmem_base + (a + 2) * kDgTileN, da + (ks * 32 >> 4), db + (ks * 32 >> 4), idesc, !(init && ks == 0));
+            }
 #pragma unroll
-                for (int ks = 0; ks < kK2BlockKBytes / 32; ++ks)
-                  umma_i8(d_tmem, da + (ks * 32 >> 4), db + (ks * 32 >> 4), idesc,
-                          !(first_pair && kb == 0 && ks == 0));
-              }
+            for (int a = 0; a < 3; ++a) {
+              const uint64_t da = umma_desc_k_sw128(a_addr + a * kDgABytes);
+              const uint64_t db = umma_desc_k_sw128(b_addr);
+#pragma unroll
+              for (int ks = 0; ks < kK2BlockKBytes / 32; ++ks)
+                umma_i8(tmem_base + a * kDgTileN, da + (ks * 32 >> 4), db + (ks * 32 >> 4), idesc2,
+                        !(init && a == 0 && ks == 0));
             }
             umma_commit(&empty[s]);
             if (kb == p.k_blocks - 1) umma_commit(tfull);
