@@ -274,7 +274,7 @@ def net_leg(kind, eng_dev, cubes, n_scans, passes, steps, rank, world, dist, str
     dev = cubes.device
     eng = Engine(dev.index)
     spec = onets.random_dnn(0) if kind == "dnn" else onets.random_sgan(0)
-    net = GpuNetClassifier(spec, engine=eng, chunk=int(os.environ.get("RML_BENCH_NET_CHUNK", "8192" if kind == "dnn" else "4096")))
+    net = GpuNetClassifier(spec, engine=eng, chunk=int(os.environ.get("RML_BENCH_NET_CHUNK", "9472" if kind == "dnn" else "4096")))   # dnn: half a dense group (148 x 128 scans): equal launches
     sub = cubes[:n_scans]
     launches0 = eng.launch_count
     out = net.predict_cubes(sub)
