@@ -63,3 +63,42 @@ def test_config1_full_size_properties(small_problem):
     assert np.array_equal(l1[sample].cpu().numpy(), lab_o)
     assert np.abs(p1[sample].cpu().numpy().astype(np.float64) - P_o).max() < 1e-5
     eng.close()
+
+
+@pytest.mark.parametrize("kind,n", [("dnn", 20000), ("sgan_c", 5000)])
+def test_network_configs_size_independent_properties(kind, n):
+    """configs[2] / configs[4] at sizes the float64 oracle cannot score in test time: the result of a
+    scan must not depend on how the batch is cut into tower chunks and dense groups (the persistent
+    tower kernel hands images between CTAs, roles and ring slots in a different order every time), nor
+    on its position in the batch; rows are distributions; a sample agrees with the oracle."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    sys.path.insert(0, ROOT)
+    from bench import device_cubes
+    from oracle import nets, synth
+    from radar_ml_b200.engine import Engine
+    from radar_ml_b200.nets import GpuNetClassifier
+    eng = Engine(0)
+    spec = nets.random_dnn(5) if kind == "dnn" else nets.random_sgan(5)
+    cubes = device_cubes(n, 41, eng.device)
+    big = GpuNetClassifier(spec, engine=eng, chunk=9472 if kind == "dnn" else 4096)
+    p1, l1 = (t.clone() for t in big.predict_cubes(cubes))
+    small = GpuNetClassifier(spec, engine=eng, chunk=1000)             # ragged chunks, other CTA / image pairing
+    p2, l2 = (t.clone() for t in small.predict_cubes(cubes))
+    assert torch.equal(p1, p2) and torch.equal(l1, l2)
+    g = torch.Generator(device="cpu").manual_seed(9)
+    idx = torch.randperm(n, generator=g)[:777].to(eng.device)
+    p3, l3 = small.predict_cubes(cubes[idx].contiguous())
+    assert torch.equal(p3, p1[idx]) and torch.equal(l3, l1[idx])
+    P = p1.double()
+    assert float((P.sum(dim=1) - 1.0).abs().max()) < 1e-5 and bool(torch.isfinite(P).all())
+    assert torch.equal(P.argmax(dim=1).int(), l1.int())
+    # oracle on a few scans (float64 with the device's bf16 rounding points)
+    m = 6
+    sample = cubes[idx[:m]].cpu().numpy()
+    xz, yz, xy = synth.project_max(sample)
+    Xn = nets.preprocess([(xz[i], yz[i], xy[i]) for i in range(m)], spec.R)
+    P_o, _ = nets.forward_bf16_towers(spec, Xn)
+    assert np.abs(p1[idx[:m]].cpu().numpy() - P_o).max() < 5e-4
+    eng.close()
