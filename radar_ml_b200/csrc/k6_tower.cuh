@@ -99,7 +99,11 @@ struct T6Smem {
   static constexpr int plane0_slots = ((kT6TH + 1) * kT6Pitch + 7) / 8 * 8 + 4, plane1_slots = (kT6TH * kT6Pitch + 7) / 8 * 8 - 4;
   static_assert(plane0_slots >= (kT6TH + 1) * kT6Pitch && plane1_slots >= kT6TH * kT6Pitch && plane0_slots % 8 == 4 && plane1_slots % 8 == 4, "plane padding");
   static constexpr int strip_slots = 2 * plane0_slots + 2 * plane1_slots + 24;     // tail: the last tile over-reads
-  static constexpr int tabs = strip + (FUSE2 ? strip_slots * 128 : 0);   // kh [R][12] | kv [R][8] f64, bh | bv [R] int2
+  // !FUSE2: every T warp stages 32 pixels x 64 channels (4 KB, 128B-swizzled rows) for one TMA store; warps
+  // 0-1 of a group use the group's im2col tile (free once its UMMAs have retired), warps 2-3 this region
+  static constexpr int stg2 = (strip + (FUSE2 ? strip_slots * 128 : 0) + 1023) & ~1023;
+  static constexpr int stg2_bytes = FUSE2 ? 0 : 4 * 2 * 4096;
+  static constexpr int tabs = FUSE2 ? strip + strip_slots * 128 : stg2 + stg2_bytes;   // kh [R][12] | kv [R][8] f64, bh | bv [R] int2
   static constexpr int tabs_bytes = R * (12 + 8) * 8 + 2 * R * 8;
   static constexpr int bias = tabs + tabs_bytes;                          // b2 [C2]
   static constexpr int bars = bias + C2 * 4;
@@ -233,7 +237,7 @@ __device__ __forceinline__ uint32_t act_pack(float a, float b, float alpha) {
 }
 
 template <int C1, bool FUSE2, int ACT>
-__global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
+__global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p, const __grid_constant__ CUtensorMap map_out) {
   using L = T6Smem<C1, FUSE2>;
   constexpr int R = L::R;
   constexpr int H1 = R / 2;               // layer-1 output size
@@ -252,6 +256,7 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
   unsigned char* w1s = smem + L::w1;
   unsigned char* w2s = smem + L::w2;
   unsigned char* strip = smem + L::strip;
+  unsigned char* stg2 = smem + L::stg2;
   double* s_kh = reinterpret_cast<double*>(smem + L::tabs);            // [12][R] (tap-major)
   double* s_kv = s_kh + R * 12;                                         // [8][R]
   int2* s_bh = reinterpret_cast<int2*>(s_kv + R * 8);
@@ -680,6 +685,13 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
           unsigned char* stg = a1 + grp * kT6A1Bytes + q * 2048;
           __nv_bfloat16* gtile = p.out + ((static_cast<int64_t>(b) * 3 + br) * H1 * H1 +
                                           static_cast<int64_t>(y1_0) * H1 + grp * 128 + q * 32) * C1;
+          // !FUSE2 (default): the warp's 32 pixels x 64 channels are staged as 128-byte rows under the 128B
+          // swizzle (conflict-free 128-bit stores) and leave as ONE tiled TMA store of full 128-byte lines
+          // (box {64 ch, 32 px} of the [pixels][C1] tensor) — no LDS / STG chain on the load/store path the
+          // resize role shares.  (RML_T6_DBG=1024 keeps the warp-transpose + STG.128 form for comparison.)
+          const bool tma_out = !FUSE2 && !(p.dbg & 1024);
+          unsigned char* stg4 = q < 2 ? a1 + grp * kT6A1Bytes + q * 4096 : stg2 + grp * 8192 + (q - 2) * 4096;
+          const int32_t pix0 = static_cast<int32_t>((static_cast<int64_t>(b) * 3 + br) * H1 * H1 + y1_0 * H1 + grp * 128 + q * 32);
 #pragma unroll
           for (int c0 = 0; c0 < C1; c0 += 32) {
             uint32_t v[32];
@@ -689,7 +701,26 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
 #pragma unroll
             for (int e = 0; e < 32; e += 2)
               pk[e >> 1] = act_pack<ACT>(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), p.alpha);
-            if (FUSE2) {
+            if (tma_out) {
+              if ((c0 & 32) == 0) {
+                // the previous store out of this staging buffer has read it (waited after the TMEM load
+                // and the conversion, which do not need the buffer)
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+              }
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(stg4 + lane * 128 + (((((c0 & 32) >> 3) + c) ^ (lane & 7)) << 4)) =
+                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+              if (c0 & 32) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&map_out, stg4, c0 - 32, pix0);
+                  bulk_commit();
+                }
+              }
+            } else if (FUSE2) {
               if (store) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
@@ -716,6 +747,9 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
         }
         tc_fence_before();
         if (!FUSE2) {
+          // warps 0-1 staged in the group's im2col tile: their TMA stores must have read it before the
+          // next round's gather overwrites it
+          if (q < 2 && lane == 0) bulk_wait_read<0>();
           bar_group(1 + grp, 128);          // the tile's TMEM and im2col buffer are free for the next round
           continue;
         }
@@ -755,6 +789,7 @@ __global__ void __launch_bounds__(kT6Threads, 1) k6_tower(const TowerParams p) {
     }
     // drain: the last strip's MMAs must retire before TMEM is released (group 0 has waited already)
     if (FUSE2 && gstrip > 0 && grp != 0) mbar_wait(mbar2, (gstrip - 1) & 1);
+    if (!FUSE2 && lane == 0) bulk_wait_all<0>();      // this warp's TMA stores have left shared memory and landed
     }
   }
   tc_fence_before();

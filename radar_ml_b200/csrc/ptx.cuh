@@ -111,6 +111,13 @@ __device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* m
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+// 2-D tiled TMA store shared -> global (UTMASTG), bulk async-group completion: the box leaves shared
+// memory in the tensor map's swizzle and lands as full rows of the global tensor.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src_smem, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
+               "r"(c0), "r"(c1), "r"(smem_u32(src_smem))
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

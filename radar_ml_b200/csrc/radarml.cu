@@ -2015,14 +2015,29 @@ static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_
     if (n.tower_mode == 1) {
       tp.w2 = reinterpret_cast<const __nv_bfloat16*>(n.convs[1].wt_bf16); tp.b2 = n.convs[1].bias3;
       tp.out = reinterpret_cast<__nv_bfloat16*>(flat);
-      k6_tower<64, true, 1><<<grid, kT6Threads, T6Smem<64, true>::total, st>>>(tp);
+      k6_tower<64, true, 1><<<grid, kT6Threads, T6Smem<64, true>::total, st>>>(tp, CUtensorMap{});
       RML_CUDA(c, cudaGetLastError());
       ++c->launches;
       return RML_OK;
     }
     tp.w2 = nullptr; tp.b2 = nullptr;
     tp.out = reinterpret_cast<__nv_bfloat16*>(ping);
-    k6_tower<128, false, 2><<<grid, kT6Threads, T6Smem<128, false>::total, st>>>(tp);
+    // layer-1 rows leave through tiled TMA stores: [pixels][128 ch] bf16, box {64 ch, 32 px}, 128B swizzle
+    CUtensorMap map_out;
+    {
+      const int h1 = n.R / 2;
+      const int64_t pixels = n_scans * 3 * h1 * h1;
+      if (pixels > 0x7fffffffll) return fail(c, RML_E_INVALID, "tower chunk too large: %lld layer-1 pixels", static_cast<long long>(pixels));
+      cuuint64_t gdim[2] = {128u, static_cast<cuuint64_t>(pixels)};
+      cuuint64_t gstr[1] = {256u};
+      cuuint32_t box[2] = {64u, 32u};
+      cuuint32_t estr[2] = {1u, 1u};
+      CUresult r = c->encode(&map_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ping, gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(c, RML_E_CUDA, "cuTensorMapEncodeTiled(tower output) failed: %d", (int)r);
+    }
+    k6_tower<128, false, 2><<<grid, kT6Threads, T6Smem<128, false>::total, st>>>(tp, map_out);
     RML_CUDA(c, cudaGetLastError());
     ++c->launches;
   }
