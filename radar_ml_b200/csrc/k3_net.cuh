@@ -440,8 +440,16 @@ constexpr int kCgMaxStages = 12;
 // r1c_nets_experiments.txt): with one tap per stage the barrier protocol alone — no TMA, no MMA —
 // cost 650 cycles per stage, 70 % of the kernel; the tensor floor of a stage is 64-128 cycles.
 constexpr int kCgTapsPerStage = 3;
+// share_kh (Wo % 8 == 0, Wo <= 32): taps kh = 0 and kh = 2 of a kernel column read the SAME input rows one
+// output row apart (input rows 2 oy and 2 (oy + 1)), so a stage is (channel block, kw) and carries ONE box of
+// TH + 1 even rows — kh = 2 is the same shared-memory tile entered Wo pixel rows (a multiple of the 1 024-byte
+// swizzle period) further down — plus the TH odd rows of kh = 1 and the three weight tiles: 36 KB of activation
+// per stage instead of 48 KB.  The kernel is bound by what the SMs pull out of L2 (432 KB per 128-pixel tile of
+// sgan's 128 -> 64 layer, ~7.7 KB/clk over the chip), so this is time: 432 -> 360 KB per tile.
+constexpr int kCgAEvenBytes = 160 * 128;     // share_kh: (TH + 1) * Wo <= 160 pixel rows of 128 B
 struct ConvGemmParams {
   int stages;             // TMA ring depth (as many stages as fit)
+  int share_kh;           // see above
   int64_t n_img;
   int Ho, Wo, Cin, Cout;
   int TH;                 // output rows per tile (TH * Wo <= 128)
@@ -452,23 +460,25 @@ struct ConvGemmParams {
   const float* bias;      // [3][Cout]
   __nv_bfloat16* out;     // [n_img][Ho][Wo][Cout]
 };
-__host__ __device__ constexpr int cg_stage_bytes(int cout) { return kCgTapsPerStage * (128 * 128 + cout * 128); }
-__host__ __device__ constexpr int cg_pick_stages(int cout) {
-  return (232448 - 1024 - 256 - 3 * 128 * 4) / cg_stage_bytes(cout) < kCgMaxStages
-             ? (232448 - 1024 - 256 - 3 * 128 * 4) / cg_stage_bytes(cout)
+__host__ __device__ constexpr int cg_stage_bytes(int cout, int share_kh = 0) {
+  return share_kh ? kCgAEvenBytes + 128 * 128 + 3 * cout * 128 : kCgTapsPerStage * (128 * 128 + cout * 128);
+}
+__host__ __device__ constexpr int cg_pick_stages(int cout, int share_kh = 0) {
+  return (232448 - 1024 - 256 - 3 * 128 * 4) / cg_stage_bytes(cout, share_kh) < kCgMaxStages
+             ? (232448 - 1024 - 256 - 3 * 128 * 4) / cg_stage_bytes(cout, share_kh)
              : kCgMaxStages;
 }
-__host__ __device__ constexpr int cg_smem_bytes(int cout, int stages) {
-  return stages * cg_stage_bytes(cout) + 1024 + 256 + 3 * 128 * 4;
+__host__ __device__ constexpr int cg_smem_bytes(int cout, int stages, int share_kh = 0) {
+  return stages * cg_stage_bytes(cout, share_kh) + 1024 + 256 + 3 * 128 * 4;
 }
 
 __global__ void __launch_bounds__(kCgThreads, 1)
 k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-              const ConvGemmParams p) {
+              const __grid_constant__ CUtensorMap map_xe, const ConvGemmParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int stage_bytes = cg_stage_bytes(p.Cout);
+  const int stage_bytes = cg_stage_bytes(p.Cout, p.share_kh);
   const int n_stages = p.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * stage_bytes);
   uint64_t* full = bars;
@@ -499,6 +509,7 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     fence_barrier_init();
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
+    if (p.share_kh) tma_prefetch_desc(&map_xe);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
@@ -517,6 +528,31 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       int oy0 = tb * p.TH;
       if (oy0 > p.Ho - p.TH) oy0 = p.Ho - p.TH;        // last block overlaps instead of being ragged
       const int br = static_cast<int>(img % 3);
+      if (p.share_kh) {
+        const int ae_bytes = (p.TH + 1) * p.Wo * 128;
+        for (int cb = 0; cb < cblocks; ++cb) {
+          for (int kw = 0; kw < 3; ++kw, ++kit) {
+            const int s = kit % n_stages;
+            mbar_wait(&empty[s], ((kit / n_stages) & 1) ^ 1);
+            if (elect_one()) {
+              unsigned char* a_dst = smem + s * stage_bytes;
+              unsigned char* b_dst = a_dst + kCgAEvenBytes + 128 * 128;
+              mbar_arrive_expect_tx(&full[s], ae_bytes + a_bytes + 3 * w_tile);
+              // even input rows 2 oy0 .. 2 (oy0 + TH) (kh = 0 and, one output row down, kh = 2), odd rows (kh = 1)
+              tma_load_4d(a_dst, &map_xe, cb * 64, kw - p.pad_l, 2 * oy0 - p.pad_t, static_cast<int32_t>(img),
+                          &full[s], pol_a);
+              tma_load_4d(a_dst + kCgAEvenBytes, &map_x, cb * 64, kw - p.pad_l, 2 * oy0 + 1 - p.pad_t,
+                          static_cast<int32_t>(img), &full[s], pol_a);
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh)
+                tma_load_2d(b_dst + kh * w_tile, &map_w, ((kh * 3 + kw) * cblocks + cb) * 64, br * p.Cout,
+                            &full[s], pol_b);
+            }
+            __syncwarp();
+          }
+        }
+        continue;
+      }
       for (int kh = 0; kh < 3; ++kh) {
         for (int cb = 0; cb < cblocks; ++cb, ++kit) {
           const int s = kit % n_stages;
@@ -551,6 +587,20 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          if (p.share_kh) {
+            const uint32_t b_addr = a_addr + kCgAEvenBytes + 128 * 128;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              const uint32_t a_off = kh == 1 ? kCgAEvenBytes : (kh == 2 ? p.Wo * 128 : 0);
+              const uint64_t da = umma_desc_k_sw128(a_addr + a_off);
+              const uint64_t db = umma_desc_k_sw128(b_addr + kh * w_tile);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_f16(d_tmem, da + (ks * 32 >> 4), db + (ks * 32 >> 4), idesc, (kb | kh | ks) != 0);
+            }
+            umma_commit(&empty[s]);
+            if (kb == k_stages - 1) umma_commit(&tfull[ab]);
+          } else {
           const uint32_t b_addr = a_addr + kCgTapsPerStage * 128 * 128;
 #pragma unroll
           for (int kw = 0; kw < kCgTapsPerStage; ++kw) {
@@ -562,6 +612,7 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           }
           umma_commit(&empty[s]);
           if (kb == k_stages - 1) umma_commit(&tfull[ab]);
+          }
         }
         __syncwarp();
       }

@@ -148,6 +148,7 @@ struct Net {
   float* t6_b1 = nullptr;      // [3][C1]
   int t6_ctas[3] = {0, 0, 0};
   int t6_dbg = 0;              // RML_T6_DBG timing experiments (results are wrong when set)
+  bool k4_share = true;        // k4_conv_igemm: kh = 0 / kh = 2 from one activation box (RML_K4_SHARE=0: one box per tap)
 };
 
 }  // namespace
@@ -1887,6 +1888,7 @@ int rml_net_finish(rml_ctx* c) {
     if ((rc = upload(c, &n.t6_b1, b1.data(), b1.size()))) return rc;
     // persistent CTAs per branch, proportional to the per-image cost (resize rows differ: 22 / 31 / 22)
     if (const char* e = getenv("RML_T6_DBG")) n.t6_dbg = atoi(e);
+    if (const char* e = getenv("RML_K4_SHARE")) n.k4_share = atoi(e) != 0;
     int split[3] = {50, 52, 46};
     if (const char* e = getenv("RML_T6_SPLIT")) sscanf(e, "%d,%d,%d", &split[0], &split[1], &split[2]);
     const int tot = split[0] + split[1] + split[2];
@@ -2112,11 +2114,21 @@ static int net_towers_chunk(rml_ctx* c, const float* feats, const float* images_
       gp.tiles_per_img = (ho + th - 1) / th; gp.pad_t = pad; gp.pad_l = pad;
       gp.act = cv.act; gp.alpha = n.alpha; gp.bias = cv.bias3;
       gp.out = reinterpret_cast<__nv_bfloat16*>(dst);
-      gp.stages = cg_pick_stages(cv.cout);
-      const int smem = cg_smem_bytes(cv.cout, gp.stages);
+      // taps kh = 0 / kh = 2 from one box of TH + 1 even rows (see ConvGemmParams::share_kh)
+      gp.share_kh = (ho % 8 == 0 && ho <= 32 && th * ho <= 128 && ho % th == 0 && n.k4_share) ? 1 : 0;
+      CUtensorMap map_xe = map_x;
+      if (gp.share_kh) {
+        cuuint32_t box_e[4] = {64u, static_cast<cuuint32_t>(2 * ho), static_cast<cuuint32_t>(2 * (th + 1)), 1u};
+        r = c->encode(&map_xe, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(cur), gdim, gstr,
+                      box_e, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(c, RML_E_CUDA, "cuTensorMapEncodeTiled(conv activation, even rows) failed: %d", (int)r);
+      }
+      gp.stages = cg_pick_stages(cv.cout, gp.share_kh);
+      const int smem = cg_smem_bytes(cv.cout, gp.stages, gp.share_kh);
       const int64_t tiles = gp.n_img * gp.tiles_per_img;
       const int grid = static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
-      k4_conv_igemm<<<grid, kCgThreads, smem, st>>>(map_x, cv.map_w, gp);
+      k4_conv_igemm<<<grid, kCgThreads, smem, st>>>(map_x, cv.map_w, map_xe, gp);
     } else if (cv.cin == 1 && n.use_igemm && (cv.cout == 64 || cv.cout == 128)) {
       Conv1Params c1;
       c1.in = static_cast<const float*>(cur);
