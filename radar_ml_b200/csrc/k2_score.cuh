@@ -217,7 +217,7 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
     // the feature tile is re-read once per support-vector chunk: keep it in L2 until then
     const uint64_t pol_a = p.n_chunks > 1 ? policy_evict_last() : policy_evict_first();
     const uint64_t pol_b = policy_evict_last();
-    uint32_t kit = 0;
+    uint32_t kit = 0, rs = 0, rph = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       if (p.tile_ready) {
         // fused pipeline: the projection kernel is still running on the other SMs; wait
@@ -229,8 +229,9 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
       }
       for (int ch = 0; ch < p.n_chunks; ++ch) {
         for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
-          const int s = kit % kK2Stages;
-          mbar_wait(&empty[s], ((kit / kK2Stages) & 1) ^ 1);
+          const int s = static_cast<int>(rs);           // ring slot and its phase, carried (no runtime division)
+          mbar_wait(&empty[s], rph ^ 1u);
+          if (++rs == static_cast<uint32_t>(kK2Stages)) { rs = 0; rph ^= 1u; }
           if (elect_one()) {
             unsigned char* a_dst = smem + s * stage_bytes;
             unsigned char* b_dst = a_dst + kK2BlockM * kK2BlockKBytes;
@@ -246,7 +247,7 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma_idesc(kCS32, kFmtU8, kFmtU8, kK2BlockM, p.n_tile);
-    uint32_t kit = 0, ait = 0;
+    uint32_t kit = 0, ait = 0, rs = 0, rph = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int ch = 0; ch < p.n_chunks; ++ch, ++ait) {
         const int ab = ait & 1;
@@ -254,8 +255,9 @@ k2_rbf_i8(const __grid_constant__ CUtensorMap map_feats, const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * kK2MaxTileN;
         for (int kb = 0; kb < p.k_blocks; ++kb, ++kit) {
-          const int s = kit % kK2Stages;
-          mbar_wait(&full[s], (kit / kK2Stages) & 1);
+          const int s = static_cast<int>(rs);
+          mbar_wait(&full[s], rph);
+          if (++rs == static_cast<uint32_t>(kK2Stages)) { rs = 0; rph ^= 1u; }
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_addr = smem_u32(smem + s * stage_bytes);

@@ -521,7 +521,7 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     // whole warp in uniform control flow, one elected lane issues (see elect_one())
     const uint64_t pol_a = policy_evict_last();    // every activation pixel is read ~2.25 times
     const uint64_t pol_b = policy_evict_last();
-    uint32_t kit = 0;
+    uint32_t kit = 0, rs = 0, rph = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t img = tile / p.tiles_per_img;
       const int tb = static_cast<int>(tile - img * p.tiles_per_img);
@@ -532,8 +532,9 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         const int ae_bytes = (p.TH + 1) * p.Wo * 128;
         for (int cb = 0; cb < cblocks; ++cb) {
           for (int kw = 0; kw < 3; ++kw, ++kit) {
-            const int s = kit % n_stages;
-            mbar_wait(&empty[s], ((kit / n_stages) & 1) ^ 1);
+            const int s = static_cast<int>(rs);           // ring slot and its phase, carried (no runtime division)
+            mbar_wait(&empty[s], rph ^ 1u);
+            if (++rs == static_cast<uint32_t>(n_stages)) { rs = 0; rph ^= 1u; }
             if (elect_one()) {
               unsigned char* a_dst = smem + s * stage_bytes;
               unsigned char* b_dst = a_dst + kCgAEvenBytes + 128 * 128;
@@ -555,8 +556,9 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       }
       for (int kh = 0; kh < 3; ++kh) {
         for (int cb = 0; cb < cblocks; ++cb, ++kit) {
-          const int s = kit % n_stages;
-          mbar_wait(&empty[s], ((kit / n_stages) & 1) ^ 1);
+          const int s = static_cast<int>(rs);           // ring slot and its phase, carried (no runtime division)
+          mbar_wait(&empty[s], rph ^ 1u);
+          if (++rs == static_cast<uint32_t>(n_stages)) { rs = 0; rph ^= 1u; }
           if (elect_one()) {
             unsigned char* a_dst = smem + s * stage_bytes;
             unsigned char* b_dst = a_dst + kCgTapsPerStage * 128 * 128;
@@ -575,15 +577,16 @@ k4_conv_igemm(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     }
   } else if (warp == 1) {
     const uint32_t idesc = umma_idesc(kCF32, kFmtBF16, kFmtBF16, 128, p.Cout);
-    uint32_t kit = 0, ait = 0;
+    uint32_t kit = 0, ait = 0, rs = 0, rph = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ait) {
       const int ab = ait & 1;
       mbar_wait(&tempty[ab], ((ait >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + ab * 128;
       for (int kb = 0; kb < k_stages; ++kb, ++kit) {
-        const int s = kit % n_stages;
-        mbar_wait(&full[s], (kit / n_stages) & 1);
+        const int s = static_cast<int>(rs);
+        mbar_wait(&full[s], rph);
+        if (++rs == static_cast<uint32_t>(n_stages)) { rs = 0; rph ^= 1u; }
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -754,11 +757,12 @@ k5_dense_stack(const __grid_constant__ CUtensorMap map_act, const __grid_constan
     // whole warp in uniform control flow, one elected lane issues (see elect_one())
     const uint64_t pol_a = policy_evict_first();
     const uint64_t pol_b = policy_evict_last();
-    uint32_t kit = 0;
+    uint32_t kit = 0, rs = 0, rph = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int ks = 0; ks < k_steps; ++ks, ++kit) {
-        const int s = kit % n_st;
-        mbar_wait(&empty[s], ((kit / n_st) & 1) ^ 1);
+        const int s = static_cast<int>(rs);           // ring slot and its phase, carried (no runtime division)
+        mbar_wait(&empty[s], rph ^ 1u);
+        if (++rs == static_cast<uint32_t>(n_st)) { rs = 0; rph ^= 1u; }
         if (elect_one()) {
           unsigned char* a_dst = smem + s * st_bytes;
           unsigned char* b_dst = a_dst + kpg * kABytes;
@@ -775,15 +779,16 @@ k5_dense_stack(const __grid_constant__ CUtensorMap map_act, const __grid_constan
     }
   } else if (warp == 1) {
     const uint32_t idesc = umma_idesc(kCF32, kFmtBF16, kFmtBF16, kK5BlockM, kK5N);
-    uint32_t kit = 0, ait = 0;
+    uint32_t kit = 0, ait = 0, rs = 0, rph = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ait) {
       const int ab = ait & 1;
       mbar_wait(&tempty[ab], ((ait >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + ab * kK5N;
       for (int ks = 0; ks < k_steps; ++ks, ++kit) {
-        const int s = kit % n_st;
-        mbar_wait(&full[s], (kit / n_st) & 1);
+        const int s = static_cast<int>(rs);
+        mbar_wait(&full[s], rph);
+        if (++rs == static_cast<uint32_t>(n_st)) { rs = 0; rph ^= 1u; }
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * st_bytes);
