@@ -108,3 +108,28 @@ def test_predict_cubes_slice_mode_and_batch_invariance(eng):
     perm = torch.randperm(70)
     p_perm, _ = net.predict_cubes(d[perm].contiguous(), mode="slice", ijk=torch.from_numpy(ijk)[perm].cuda())
     assert torch.equal(p_perm.cpu(), p.cpu()[perm])
+
+
+def test_sgan_kernel_forms_agree(eng, monkeypatch):
+    """Two round-2 rewrites of the sgan path against the forms they replaced (selected when the
+    network is loaded): the tower's tiled TMA stores against the warp transpose + STG.128 form
+    (RML_T6_DBG=1024: same arithmetic, so the results are bit-identical) and the implicit GEMM's
+    shared kh = 0 / kh = 2 activation box against one box per tap (RML_K4_SHARE=0: another fp32
+    accumulation order, so equal to 1e-6).  337 scans: ragged chunks and a partial last tile."""
+    import torch
+    from oracle import nets, synth
+    from radar_ml_b200.nets import GpuNetClassifier
+    spec = nets.random_sgan(11)
+    cubes, _, _ = synth.make_cubes(337, seed=62)
+    d = torch.from_numpy(cubes).cuda()
+    p_new, l_new = (t.clone() for t in GpuNetClassifier(spec, engine=eng, chunk=100).predict_cubes(d))
+    monkeypatch.setenv("RML_T6_DBG", "1024")
+    p_stg, l_stg = (t.clone() for t in GpuNetClassifier(spec, engine=eng, chunk=100).predict_cubes(d))
+    monkeypatch.delenv("RML_T6_DBG")
+    assert torch.equal(p_new, p_stg) and torch.equal(l_new, l_stg)
+    monkeypatch.setenv("RML_K4_SHARE", "0")
+    p_tap, l_tap = (t.clone() for t in GpuNetClassifier(spec, engine=eng, chunk=100).predict_cubes(d))
+    monkeypatch.delenv("RML_K4_SHARE")
+    assert float((p_new - p_tap).abs().max()) < 1e-6
+    # restore the default forms for whoever uses the shared engine next
+    GpuNetClassifier(spec, engine=eng, chunk=100)
