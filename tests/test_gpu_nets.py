@@ -115,7 +115,9 @@ def test_sgan_kernel_forms_agree(eng, monkeypatch):
     network is loaded): the tower's tiled TMA stores against the warp transpose + STG.128 form
     (RML_T6_DBG=1024: same arithmetic, so the results are bit-identical) and the implicit GEMM's
     shared kh = 0 / kh = 2 activation box against one box per tap (RML_K4_SHARE=0: another fp32
-    accumulation order, so equal to 1e-6).  337 scans: ragged chunks and a partial last tile."""
+    accumulation order; a layer-2 value on a bf16 rounding boundary may then round the other way, the
+    same effect that sets the 5e-4 end-to-end bound above — measured 2e-5).  337 scans: ragged chunks
+    and a partial last tile."""
     import torch
     from oracle import nets, synth
     from radar_ml_b200.nets import GpuNetClassifier
@@ -130,6 +132,9 @@ def test_sgan_kernel_forms_agree(eng, monkeypatch):
     monkeypatch.setenv("RML_K4_SHARE", "0")
     p_tap, l_tap = (t.clone() for t in GpuNetClassifier(spec, engine=eng, chunk=100).predict_cubes(d))
     monkeypatch.delenv("RML_K4_SHARE")
-    assert float((p_new - p_tap).abs().max()) < 1e-6
+    assert float((p_new - p_tap).abs().max()) < 2e-4
+    srt = p_new.sort(dim=1).values
+    clear = (srt[:, -1] - srt[:, -2]) > 1e-3
+    assert torch.equal(l_new[clear], l_tap[clear])
     # restore the default forms for whoever uses the shared engine next
     GpuNetClassifier(spec, engine=eng, chunk=100)
