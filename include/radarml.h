@@ -188,12 +188,14 @@ int rml_predict_host(rml_ctx* ctx, const float* cubes_host, int64_t B, int mode,
  * 0..255 to float32): for a model on the integer path each chunk is converted back to bytes on the
  * host (a pool of threads, every value checked to be exactly an integer in [0,255]) and a quarter
  * of the bytes crosses PCIe; the device runs the uint8-cube kernels, whose results are identical bit
- * for bit.  A chunk holding any other value is copied as float32 as before.  OFF by default (env
- * RML_HOST_NARROW=1 enables): it pays only where the host converts faster than the bus moves float32
- * bytes — on the B200 box (16 vCPUs, PCIe 5 x16) the conversion runs at 65-90 GB/s of float32 input
- * against 53 GB/s over the bus, +3 % end to end (bench.py e2e.host_narrowing) — and it switches
- * itself off when the conversion falls below min_gbs (default 60).  threads = 0: one per CPU of the
- * process's affinity mask.  Call before rml_reserve(RML_RESERVE_HOST). */
+ * for bit.  A chunk holding any other value is copied as float32 as before (two such chunks switch
+ * the check off).  ON by default (env RML_HOST_NARROW=0 or enabled = 0 disables): the conversion of
+ * chunk n+1 overlaps the copy and the kernels of chunk n — results leave through pinned mirrors, so
+ * no copy blocks the calling thread — and it pays where the host converts faster than the bus moves
+ * float32 bytes: on the B200 box (16 vCPUs, PCIe 5 x16) 65-95 GB/s of float32 input against 53 GB/s
+ * over the bus, 113 k -> 140-145 k scans/s end to end (bench.py e2e / e2e.plain_copy).  It switches
+ * itself off when three consecutive chunks convert slower than min_gbs (default 60).  threads = 0:
+ * one per CPU of the process's affinity mask.  Call before rml_reserve(RML_RESERVE_HOST). */
 int rml_set_host_narrowing(rml_ctx* ctx, int enabled, int threads, double min_gbs);
 /* the conversion itself (host only, no GPU needed): dst_host[i] = (uint8_t)src_host[i]; RML_OK when every
  * value is exactly an integer in [0,255], RML_E_NONINTEGRAL otherwise.  dst_host 32-byte aligned. */

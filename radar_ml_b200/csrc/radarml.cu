@@ -74,6 +74,13 @@ struct HostPipe {
   uint8_t* known[kHostBufs] = {nullptr};
   cudaStream_t stream[kHostBufs] = {nullptr};
   size_t work_bytes = 0;
+  // results leave through pinned mirrors: a cudaMemcpyAsync into the caller's (pageable) arrays blocks the
+  // host thread until the stream has drained, which serialised the host-side work of chunk n+1 (the
+  // narrowing below) behind the copy and the kernels of chunk n
+  unsigned char* res_pin[kHostBufs] = {nullptr};   // [chunk][C floats | int32 label | u8 known]
+  cudaEvent_t res_ev[kHostBufs] = {nullptr};       // the D2H copies into res_pin[i] have finished
+  int64_t res_at[kHostBufs] = {0}, res_n[kHostBufs] = {0};   // scans [res_at, res_at + res_n) wait in res_pin[i]
+  int narrow_bad = 0;              // chunks that turned out not to be integral (two of them switch narrowing off)
   // host-side narrowing of integral float32 cubes to bytes before the H2D copy (host_narrow.h)
   uint8_t* narrow_pin[kHostBufs] = {nullptr};      // pinned staging, chunk x cube elements each
   cudaEvent_t narrow_ev[kHostBufs] = {nullptr};    // the H2D copy out of a staging buffer has finished
@@ -166,8 +173,10 @@ struct rml_ctx {
   std::vector<double> aff_shift;  // offset[f] / scale[f]: makes standardised features non-negative (digit path)
   int k1_split = 1, k5_kpg = 0;   // tuning experiments (RML_K1_SPLIT, RML_K5_KPG), read once at create
   int force_f32 = 0;              // rml_set_precision: 1 = float32 features even for an integral model
-  int host_narrow = 0;            // rml_predict_host: integral float32 cubes cross the bus as bytes (rml_set_host_narrowing;
-                                  // off by default: on the B200 box the host converts at 65-90 GB/s, what PCIe moves anyway)
+  int host_narrow = 1;            // rml_predict_host: integral float32 cubes cross the bus as bytes (rml_set_host_narrowing,
+                                  // RML_HOST_NARROW=0).  On by default since the results leave through pinned mirrors: the
+                                  // conversion of chunk n+1 (65-95 GB/s on the 16-vCPU B200 box) then really overlaps the copy
+                                  // and the kernels of chunk n: 113 k -> 140-145 k scans/s end to end
   int host_narrow_threads = 0;    // conversion threads (0 = one per CPU of the process's affinity mask)
   double host_narrow_min_gbs = 60.0;
   void* nccl_comm = nullptr;
@@ -686,6 +695,8 @@ void free_pipe(HostPipe& hp) {
     cudaFree(hp.cubes[i]); cudaFree(hp.ijk[i]); cudaFree(hp.work[i]);
     cudaFree(hp.proba[i]); cudaFree(hp.label[i]); cudaFree(hp.known[i]);
     if (hp.stream[i]) cudaStreamDestroy(hp.stream[i]);
+    if (hp.res_pin[i]) cudaFreeHost(hp.res_pin[i]);
+    if (hp.res_ev[i]) cudaEventDestroy(hp.res_ev[i]);
     if (hp.narrow_pin[i]) cudaFreeHost(hp.narrow_pin[i]);
     if (hp.narrow_ev[i]) cudaEventDestroy(hp.narrow_ev[i]);
   }
@@ -1151,6 +1162,8 @@ int reserve_host_pipe(rml_ctx* c, int cube_u8) {
     RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.label[i]), chunk * 4));
     RML_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&hp.known[i]), chunk));
     RML_CUDA(c, cudaStreamCreateWithFlags(&hp.stream[i], cudaStreamNonBlocking));
+    RML_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&hp.res_pin[i]), chunk * (kMaxClasses * 4 + 4 + 1), cudaHostAllocDefault));
+    RML_CUDA(c, cudaEventCreateWithFlags(&hp.res_ev[i], cudaEventDisableTiming));
   }
   hp.chunk = chunk;
   hp.cube_bytes = cube_bytes;
@@ -1225,10 +1238,24 @@ int predict_host_impl(rml_ctx* c, const void* cubes_host, int cube_u8, int64_t B
   const size_t cube_elems = cube_bytes / (cube_u8 ? 1 : 4);
   hp.last_h2d_bytes = 0;
   hp.last_narrowed = 0;
+  // results of the chunk that used a slot before: pinned mirror -> the caller's arrays
+  auto drain = [&](int sl) -> int {
+    if (!hp.res_n[sl]) return RML_OK;
+    RML_CUDA(c, cudaEventSynchronize(hp.res_ev[sl]));
+    const int64_t at = hp.res_at[sl], m = hp.res_n[sl];
+    const unsigned char* r = hp.res_pin[sl];
+    memcpy(proba_host + at * C, r, static_cast<size_t>(m) * C * 4);
+    memcpy(label_host + at, r + chunk * kMaxClasses * 4, static_cast<size_t>(m) * 4);
+    if (known_host) memcpy(known_host + at, r + chunk * (kMaxClasses * 4 + 4), static_cast<size_t>(m));
+    hp.res_n[sl] = 0;
+    return RML_OK;
+  };
+  for (int i = 0; i < kHostBufs; ++i) hp.res_n[i] = 0;
   while (done < B) {
     const int64_t n = (B - done) < chunk ? (B - done) : chunk;
     cudaStream_t st = hp.stream[slot];
     int as_u8 = cube_u8;
+    { int rc = drain(slot); if (rc) return rc; }
     if (narrow && !hp.narrow_off && n >= 32) {      // a few scans are quicker to copy than to hand to the pool
       const auto tw = std::chrono::steady_clock::now();
       RML_CUDA(c, cudaEventSynchronize(hp.narrow_ev[slot]));     // the previous copy out of this staging buffer
@@ -1248,6 +1275,7 @@ int predict_host_impl(rml_ctx* c, const void* cubes_host, int cube_u8, int64_t B
         hp.narrow_slow = hp.narrow_gbs < c->host_narrow_min_gbs ? hp.narrow_slow + 1 : 0;
         if (hp.narrow_slow >= 3) hp.narrow_off = true;
       }
+      if (bad && ++hp.narrow_bad >= 2) hp.narrow_off = true;     // real-valued cubes: stop paying for the check
       if (!bad) {
         RML_CUDA(c, cudaMemcpyAsync(hp.cubes[slot], hp.narrow_pin[slot], static_cast<size_t>(n) * cube_elems,
                                     cudaMemcpyHostToDevice, st));
@@ -1267,12 +1295,19 @@ int predict_host_impl(rml_ctx* c, const void* cubes_host, int cube_u8, int64_t B
     int rc = predict_impl(c, hp.cubes[slot], n, mode, hp.ijk[slot], mask, min_proba, hp.work[slot],
                           hp.proba[slot], hp.label[slot], hp.known[slot], st, as_u8);
     if (rc) return rc;
-    RML_CUDA(c, cudaMemcpyAsync(proba_host + done * C, hp.proba[slot], n * C * 4, cudaMemcpyDeviceToHost, st));
-    RML_CUDA(c, cudaMemcpyAsync(label_host + done, hp.label[slot], n * 4, cudaMemcpyDeviceToHost, st));
+    unsigned char* r = hp.res_pin[slot];
+    RML_CUDA(c, cudaMemcpyAsync(r, hp.proba[slot], n * C * 4, cudaMemcpyDeviceToHost, st));
+    RML_CUDA(c, cudaMemcpyAsync(r + chunk * kMaxClasses * 4, hp.label[slot], n * 4, cudaMemcpyDeviceToHost, st));
     if (known_host)
-      RML_CUDA(c, cudaMemcpyAsync(known_host + done, hp.known[slot], n, cudaMemcpyDeviceToHost, st));
+      RML_CUDA(c, cudaMemcpyAsync(r + chunk * (kMaxClasses * 4 + 4), hp.known[slot], n, cudaMemcpyDeviceToHost, st));
+    RML_CUDA(c, cudaEventRecord(hp.res_ev[slot], st));
+    hp.res_at[slot] = done; hp.res_n[slot] = n;
     done += n;
     slot = (slot + 1) % kHostBufs;
+  }
+  for (int i = 0; i < kHostBufs; ++i) {
+    int rc = drain(i);
+    if (rc) return rc;
   }
   for (int i = 0; i < kHostBufs; ++i) RML_CUDA(c, cudaStreamSynchronize(hp.stream[i]));
   return RML_OK;
