@@ -384,3 +384,31 @@ def test_allgather_labels_two_ranks():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "DIST_OK" in res.stdout
+
+
+def test_predict_host_many_chunks_through_pinned_result_mirrors(eng, small_problem):
+    """rml_predict_host with more chunks than staging slots (3): the results of a chunk wait in a pinned
+    mirror until its slot comes round again, so every slot is drained, reused and drained at the end.
+    2 100 float32 scans = 5 chunks (4 x 512 + 52), as uint8 3 chunks (2 x 1 024 + 52); each host result
+    must equal the device-resident call bit for bit, with the narrowing on (the default) and off, with
+    and without the `known` output, and a second call must not see leftovers of the first."""
+    import torch
+    from radar_ml_b200.model import from_sklearn
+    eng.load_model(from_sklearn(small_problem["cal"]))
+    base = small_problem["cubes"][300:]
+    reps = -(-2100 // base.shape[0])
+    cubes = np.ascontiguousarray(np.concatenate([base] * reps)[:2100])
+    cubes[1::2] = cubes[1::2][:, ::-1].copy()            # not periodic with the chunk size
+    Pd, ld, kd = (t.cpu().numpy() for t in eng.predict(torch.from_numpy(cubes).cuda()))
+    eng.check_status()
+    for narrowing in (True, False):
+        eng.set_host_narrowing(narrowing, threads=4, min_gbs=1e-3)
+        P, l, k = eng.predict_host(cubes)
+        assert eng.last_host_transfer()["narrowed_scans"] == (2100 if narrowing else 0)
+        assert np.array_equal(P, Pd) and np.array_equal(l, ld) and np.array_equal(k, kd.astype(np.uint8))
+        # shorter second call into the same output arrays: rows beyond it keep the first call's values
+        P2, l2, k2 = eng.predict_host(cubes[:600], out=(P, l, k))
+        assert np.array_equal(P2, Pd) and np.array_equal(l2, ld)
+    P8, l8, k8 = eng.predict_host(cubes.astype(np.uint8))
+    assert np.array_equal(P8, Pd) and np.array_equal(l8, ld) and np.array_equal(k8, kd.astype(np.uint8))
+    eng.set_host_narrowing(False)
