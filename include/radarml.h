@@ -194,7 +194,7 @@ int rml_predict_host(rml_ctx* ctx, const float* cubes_host, int64_t B, int mode,
  * no copy blocks the calling thread — and it pays where the host converts faster than the bus moves
  * float32 bytes: on the B200 box (16 vCPUs, PCIe 5 x16) 65-95 GB/s of float32 input against 53 GB/s
  * over the bus, 113 k -> 140-145 k scans/s end to end (bench.py e2e / e2e.plain_copy).  It switches
- * itself off when three consecutive chunks convert slower than min_gbs (default 60).  threads = 0:
+ * itself off when three consecutive chunks convert slower than min_gbs (default 57).  threads = 0:
  * one per CPU of the process's affinity mask.  Call before rml_reserve(RML_RESERVE_HOST). */
 int rml_set_host_narrowing(rml_ctx* ctx, int enabled, int threads, double min_gbs);
 /* the conversion itself (host only, no GPU needed): dst_host[i] = (uint8_t)src_host[i]; RML_OK when every

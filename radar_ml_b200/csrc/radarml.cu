@@ -178,7 +178,7 @@ struct rml_ctx {
                                   // conversion of chunk n+1 (65-95 GB/s on the 16-vCPU B200 box) then really overlaps the copy
                                   // and the kernels of chunk n: 113 k -> 140-145 k scans/s end to end
   int host_narrow_threads = 0;    // conversion threads (0 = one per CPU of the process's affinity mask)
-  double host_narrow_min_gbs = 60.0;
+  double host_narrow_min_gbs = 57.0;   // break-even against ~53-55 GB/s of PCIe 5 x16 plus the per-chunk launch work
   void* nccl_comm = nullptr;
   int nccl_rank = 0, nccl_world = 1;
   SmallPipe small;

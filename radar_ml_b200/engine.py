@@ -108,7 +108,7 @@ class Engine:
     def set_host_narrowing(self, enabled=True, threads=0, min_gbs=0.0):
         """``predict_host`` on float32 cubes of the sensor's integers: convert each chunk to bytes on
         the host (thread pool, exactness checked) so a quarter of the bytes crosses PCIe.  On by
-        default; it switches itself off when the host converts slower than ``min_gbs`` (60 GB/s:
+        default; it switches itself off when the host converts slower than ``min_gbs`` (57 GB/s:
         a host that cannot beat the bus) or the cubes turn out not to be integral."""
         check(self.ctx, self.lib.rml_set_host_narrowing(self.ctx, int(bool(enabled)), int(threads), float(min_gbs)))
         self._reserved.pop(RESERVE_HOST, None)
